@@ -1,0 +1,68 @@
+// ctx.cuh -- host-side context shared by the translation units of libstoke_b200.so
+#pragma once
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+struct StepAccum {          // per-optimizer-step accumulators on the device (local shard)
+  float norm_partial;       // running sum / max over the buckets reduced so far
+  uint32_t found_inf;
+  uint32_t blocks_done;     // last-block detection counter (self-resetting)
+  uint32_t pad_;
+};
+
+struct stk_ctx {
+  int rank = 0, world = 1, device = 0;
+  int sm_count = 148;
+  std::mutex mu;
+  std::string err;
+  // peer-visible allocations made through stk_mem_alloc_shared: local ptr -> peer mappings
+  struct Shared {
+    size_t bytes;
+    void* peers[STK_MAX_WORLD];
+    bool opened;
+  };
+  std::map<void*, Shared> shared;
+  // signal pads
+  stk::SignalPad* pad_local = nullptr;
+  stk::PeerPads pads{};
+  bool comm_ready = false;
+  uint32_t blk_epoch = 0;       // block-barrier epoch (identical sequence on every rank)
+  uint32_t aux_epoch[4] = {0, 0, 0, 0};
+  // device state
+  stk_scaler_state_t* scaler_dev = nullptr;
+  StepAccum* accum_dev = nullptr;
+  float* blk_partial_dev = nullptr;   // [kMaxBlocks]
+  // pinned, mapped host scratch
+  double* host_scratch = nullptr;     // [16]
+  double* host_scratch_dev = nullptr; // device alias of host_scratch
+};
+
+extern thread_local std::string g_tls_err;
+int stk_fail(stk_ctx* ctx, int code, const std::string& msg);
+
+#define STK_CUDA(ctx, call)                                                                              \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return stk_fail(ctx, STK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+#define STK_REQUIRE(ctx, cond, msg)                                   \
+  do {                                                                \
+    if (!(cond)) return stk_fail(ctx, STK_ERR_INVALID, (msg));        \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};

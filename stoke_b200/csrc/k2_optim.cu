@@ -1,0 +1,258 @@
+// k2_optim.cu -- K2: single-pass fused optimizer step (Adam / AdamW / SGD-momentum), plus the step epilogue.
+//
+// One sweep over (grad, master, exp_avg, exp_avg_sq) does what the reference spreads over clip_grad_norm_'s scaling pass /
+// clip_grad_value_, GradScaler.step's inf gate, the ~7 foreach kernels of torch.optim.Adam and (mixed precision) the
+// fp32 -> bf16 parameter cast; in sharded (OSS / ZeRO-1) mode the updated low-precision shard is stored straight into
+// every rank's parameter buffer, which is the parameter all-gather (K3).  HBM bytes per element: read g,p,m,v (16) +
+// write p,m,v (12) [+ 2 for the bf16 copy] = 28 / 30.  The clip coefficient, the skip decision and the bias corrections
+// come from device memory, so there is no host synchronisation anywhere on the step.
+//
+// Arithmetic follows torch/optim/adam.py (_single_tensor_adam, the path torch takes on CPU -- the oracle) and
+// torch/optim/sgd.py (_single_tensor_sgd); the clip follows torch/nn/utils/clip_grad.py:165-174 (coef = max_norm /
+// (total_norm + 1e-6), clamped to 1) and :291-292 (clamp).
+#include "ctx.cuh"
+
+namespace stk {
+
+struct OptimParams {
+  float* master;
+  float* m;
+  float* v;
+  const float* grad;
+  size_t nvec;          // float4 count
+  PtrTable lp;          // low-precision / remote parameter destinations (already offset)
+  int lp_world;         // 0: none
+  int lp_rank_skip;     // lp dtype == f32 and destination == master's own buffer: skip that rank (aliased)
+  const stk_scaler_state_t* scaler;
+  PeerPads pads;
+  int rank, world;
+  uint32_t epoch;
+  int cross_rank;       // 1: start/end block barriers around the peer stores
+  // hyper-parameters (double precision on the host side, converted exactly like torch converts python scalars)
+  double lr, beta1, beta2, eps, weight_decay, momentum, dampening;
+  int kind, nesterov, maximize, clip_kind;
+  float clip_max_norm, clip_value;
+};
+
+template <int LP_DT>  // -1: none, STK_BF16, STK_F32
+__device__ __forceinline__ void store_lp(const OptimParams& p, size_t i4, const float4& x) {
+  if constexpr (LP_DT == STK_BF16) {
+    uint2 u = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+#pragma unroll 1
+    for (int d = 0; d < p.lp_world; ++d) {
+      int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
+      uint2* q = reinterpret_cast<uint2*>(p.lp.p[dst]) + i4;
+      asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(q), "r"(u.x), "r"(u.y) : "memory");
+    }
+  } else if constexpr (LP_DT == STK_F32) {
+#pragma unroll 1
+    for (int d = 0; d < p.lp_world; ++d) {
+      int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
+      if (dst == p.lp_rank_skip) continue;
+      st_stream_f4(reinterpret_cast<float*>(p.lp.p[dst]) + i4 * 4, x);
+    }
+  }
+}
+
+template <int KIND, int LP_DT>
+__global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
+  __shared__ float s_bc[4];
+  if (p.cross_rank) block_barrier_all_ranks(p.pads, p.rank, p.world, 0, p.epoch);
+
+  const bool skip = p.scaler->found_inf != 0;  // GradScaler.step: no optimizer.step() at all when any grad is inf/nan
+  if (!skip) {
+    if (threadIdx.x == 0) {
+      // bias corrections in double, exactly as the python scalars in torch/optim/adam.py:531-547
+      const double t = (double)(p.scaler->opt_steps + 1);
+      double bc1 = 1.0 - pow(p.beta1, t);
+      double bc2 = 1.0 - pow(p.beta2, t);
+      s_bc[0] = (float)(p.lr / bc1);  // step_size
+      s_bc[1] = (float)sqrt(bc2);     // bias_correction2_sqrt
+      s_bc[2] = (p.scaler->opt_steps == 0) ? 1.f : 0.f;  // SGD: first step seeds the momentum buffer with the gradient
+    }
+    __syncthreads();
+    const float step_size = s_bc[0], bc2_sqrt = s_bc[1];
+    const bool first_step = s_bc[2] != 0.f;
+
+    float coef = 1.f;
+    if (p.clip_kind == STK_CLIP_NORM) {
+      float c = p.clip_max_norm / (p.scaler->grad_norm + 1e-6f);
+      coef = fminf(c, 1.0f);
+    }
+    const float cv = p.clip_value;
+    const float b2 = (float)p.beta2, eps = (float)p.eps, wd = (float)p.weight_decay;
+    const float one_m_b1 = (float)(1.0 - p.beta1), one_m_b2 = (float)(1.0 - p.beta2);
+    const float lr = (float)p.lr, mom = (float)p.momentum, one_m_damp = (float)(1.0 - p.dampening);
+    const float decay_mul = (float)(1.0 - p.lr * p.weight_decay);  // AdamW: param.mul_(1 - lr * wd)
+
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    constexpr int U = 2;
+    for (size_t i0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < p.nvec; i0 += stride * U) {
+      float4 g[U], w[U], m[U], v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i < p.nvec) {
+          g[u] = ld_stream_f4(p.grad + i * 4);
+          w[u] = ld_stream_f4(p.master + i * 4);
+          m[u] = ld_stream_f4(p.m + i * 4);
+          if (KIND != STK_OPT_SGD) v[u] = ld_stream_f4(p.v + i * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i >= p.nvec) continue;
+        float* gp = &g[u].x; float* wp = &w[u].x; float* mp = &m[u].x; float* vp = &v[u].x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float gg = gp[k];
+          if (p.clip_kind == STK_CLIP_NORM) gg *= coef;
+          else if (p.clip_kind == STK_CLIP_VALUE) gg = fminf(fmaxf(gg, -cv), cv);
+          if (p.maximize) gg = -gg;
+          float ww = wp[k];
+          if (KIND == STK_OPT_ADAM || KIND == STK_OPT_ADAMW) {
+            if (KIND == STK_OPT_ADAMW) ww *= decay_mul;
+            else if (wd != 0.f) gg = fmaf(ww, wd, gg);          // grad.add(param, alpha=wd)
+            float mm = mp[k];
+            mm = fmaf(one_m_b1, gg - mm, mm);                    // exp_avg.lerp_(grad, 1 - beta1)
+            float vv = vp[k] * b2;
+            vv = fmaf(one_m_b2 * gg, gg, vv);                    // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+            float denom = sqrtf(vv) / bc2_sqrt + eps;
+            ww = ww - step_size * (mm / denom);                  // addcdiv_(exp_avg, denom, value=-step_size)
+            mp[k] = mm; vp[k] = vv;
+          } else {  // SGD
+            if (wd != 0.f) gg = fmaf(ww, wd, gg);
+            if (mom != 0.f) {
+              float bb = first_step ? gg : fmaf(mp[k], mom, one_m_damp * gg);
+              mp[k] = bb;
+              gg = p.nesterov ? fmaf(bb, mom, gg) : bb;
+            }
+            ww = fmaf(-lr, gg, ww);
+          }
+          wp[k] = ww;
+        }
+        st_stream_f4(p.master + i * 4, w[u]);
+        if (KIND != STK_OPT_SGD || mom != 0.f) st_stream_f4(p.m + i * 4, m[u]);
+        if (KIND != STK_OPT_SGD) st_stream_f4(p.v + i * 4, v[u]);
+        store_lp<LP_DT>(p, i, w[u]);
+      }
+    }
+  }
+  if (p.cross_rank) block_barrier_all_ranks(p.pads, p.rank, p.world, 1, p.epoch);
+}
+
+// scaler.update() (torch/amp/grad_scaler.py:549-556 -> _amp_update_scale_), step counters, per-step accumulator reset
+__global__ void k_step_epilogue(stk_scaler_state_t* st, StepAccum* acc) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool inf = st->found_inf != 0;
+  if (inf) st->skipped_steps += 1;
+  else st->opt_steps += 1;
+  if (st->enabled) {
+    if (inf) {
+      st->scale = st->scale * st->backoff_factor;
+      st->growth_tracker = 0;
+    } else {
+      int t = st->growth_tracker + 1;
+      if (t == st->growth_interval) {
+        float ns = st->scale * st->growth_factor;
+        if (finitef(ns)) st->scale = ns;   // _amp_update_scale_: do not grow past the largest finite fp32
+        t = 0;
+      }
+      st->growth_tracker = t;
+    }
+  }
+  st->found_inf = 0;
+  acc->norm_partial = 0.f;
+  acc->found_inf = 0u;
+}
+
+}  // namespace stk
+
+using namespace stk;
+
+template <int KIND>
+static cudaError_t launch_optim(const OptimParams& p, int lp_dtype, int grid, bool coop, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = coop ? 1 : 0;
+  if (p.lp_world == 0) return cudaLaunchKernelEx(&cfg, k_optim_step<KIND, -1>, p);
+  if (lp_dtype == STK_BF16) return cudaLaunchKernelEx(&cfg, k_optim_step<KIND, STK_BF16>, p);
+  return cudaLaunchKernelEx(&cfg, k_optim_step<KIND, STK_F32>, p);
+}
+
+extern "C" {
+
+int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float* exp_avg, float* exp_avg_sq,
+                   const float* grad, size_t n_local, void* const* lp_ptrs, int lp_world, int lp_dtype, size_t lp_offset,
+                   void* stream) {
+  STK_REQUIRE(c, c && h && master && grad, "stk_optim_step: NULL argument");
+  STK_REQUIRE(c, n_local % 4 == 0, "stk_optim_step: n_local must be a multiple of 4");
+  STK_REQUIRE(c, h->kind >= STK_OPT_ADAM && h->kind <= STK_OPT_SGD, "stk_optim_step: bad optimizer kind");
+  STK_REQUIRE(c, h->kind == STK_OPT_SGD || (exp_avg && exp_avg_sq), "stk_optim_step: Adam needs exp_avg and exp_avg_sq");
+  STK_REQUIRE(c, !(h->kind == STK_OPT_SGD && h->momentum != 0.0 && !exp_avg), "stk_optim_step: SGD momentum needs a buffer");
+  STK_REQUIRE(c, lp_ptrs == nullptr || lp_world == 1 || lp_world == c->world, "stk_optim_step: lp_world must be 1 or world");
+  STK_REQUIRE(c, lp_ptrs == nullptr || lp_dtype == STK_BF16 || lp_dtype == STK_F32, "stk_optim_step: lp dtype");
+  if (n_local == 0 && c->world == 1) return STK_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+  OptimParams p{};
+  p.master = master;
+  p.m = exp_avg;
+  p.v = exp_avg_sq;
+  p.grad = grad;
+  p.nvec = n_local / 4;
+  p.lp_world = lp_ptrs ? lp_world : 0;
+  p.lp_rank_skip = -1;
+  const size_t esz = lp_dtype == STK_BF16 ? 2 : 4;
+  for (int r = 0; r < p.lp_world; ++r) {
+    STK_REQUIRE(c, lp_ptrs[r] != nullptr, "stk_optim_step: NULL lp pointer");
+    p.lp.p[r] = static_cast<char*>(lp_ptrs[r]) + lp_offset * esz;
+    if (lp_dtype == STK_F32 && p.lp.p[r] == static_cast<void*>(master)) p.lp_rank_skip = r;
+  }
+  p.scaler = c->scaler_dev;
+  p.pads = c->pads;
+  p.rank = c->rank;
+  p.world = c->world;
+  p.cross_rank = (p.lp_world > 1) ? 1 : 0;
+  if (p.cross_rank && !c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_optim_step (sharded) before stk_comm_connect");
+  p.epoch = p.cross_rank ? ++c->blk_epoch : 0;
+  p.lr = h->lr; p.beta1 = h->beta1; p.beta2 = h->beta2; p.eps = h->eps; p.weight_decay = h->weight_decay;
+  p.momentum = h->momentum; p.dampening = h->dampening;
+  p.kind = h->kind; p.nesterov = h->nesterov; p.maximize = h->maximize; p.clip_kind = h->clip_kind;
+  p.clip_max_norm = (float)h->clip_max_norm;
+  p.clip_value = (float)h->clip_value;
+
+  size_t want = (p.nvec + 511) / 512;  // 256 threads x 2 float4 per iteration
+  int grid;
+  if (p.cross_rank) grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 2));
+  else grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
+  if (grid > kMaxBlocks) grid = kMaxBlocks;
+
+  cudaError_t err;
+  switch (h->kind) {
+    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(p, lp_dtype, grid, p.cross_rank, s); break;
+    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(p, lp_dtype, grid, p.cross_rank, s); break;
+    default: err = launch_optim<STK_OPT_SGD>(p, lp_dtype, grid, p.cross_rank, s); break;
+  }
+  if (err != cudaSuccess) return stk_fail(c, STK_ERR_CUDA, std::string("k_optim_step launch: ") + cudaGetErrorString(err));
+  return STK_OK;
+}
+
+int stk_step_epilogue(stk_ctx* c, void* stream) {
+  STK_REQUIRE(c, c != nullptr, "stk_step_epilogue: NULL ctx");
+  DeviceGuard g(c->device);
+  k_step_epilogue<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->scaler_dev, c->accum_dev);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+}  // extern "C"
