@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
         if (i < p.nvec) {
           g[u] = ld_stream_f4(p.grad + i * 4);
           w[u] = ld_stream_f4(p.master + i * 4);
-          m[u] = ld_stream_f4(p.m + i * 4);
+          if (KIND != STK_OPT_SGD || mom != 0.f) m[u] = ld_stream_f4(p.m + i * 4);
           if (KIND != STK_OPT_SGD) v[u] = ld_stream_f4(p.v + i * 4);
         }
       }

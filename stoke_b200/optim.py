@@ -12,7 +12,7 @@ from . import _lib
 from .engine import ClipSpec, Engine, GradPath
 
 _KINDS = {torch.optim.Adam: _lib.OPT_ADAM, torch.optim.AdamW: _lib.OPT_ADAMW, torch.optim.SGD: _lib.OPT_SGD}
-_REJECT_TRUE = ("amsgrad", "capturable", "differentiable", "decoupled_weight_decay")
+_REJECT_TRUE = ("amsgrad", "capturable", "differentiable")
 
 
 class B200FusedOptimizer(torch.optim.Optimizer):
@@ -29,6 +29,8 @@ class B200FusedOptimizer(torch.optim.Optimizer):
             if defaults.get(k):
                 raise NotImplementedError(f"Stoke -- optimizer option {k}=True is not supported by the fused step")
         self._kind = _KINDS[optim_cls]
+        if defaults.get("decoupled_weight_decay"):  # torch >= 2.6: AdamW is Adam(decoupled_weight_decay=True)
+            self._kind = _lib.OPT_ADAMW
         self._torch_cls = optim_cls
         params = [p for p in module.parameters() if p.requires_grad]
         sgd = self._kind == _lib.OPT_SGD
@@ -36,6 +38,8 @@ class B200FusedOptimizer(torch.optim.Optimizer):
                              module=module, needs_second_moment=not sgd,
                              needs_first_moment=(not sgd) or defaults.get("momentum", 0) != 0)
         super().__init__(params, defaults)
+        # the step counters live in the engine's device state (one live optimizer per engine/process)
+        engine.scaler_set(opt_steps=0, skipped_steps=0, found_inf=0, growth_tracker=0)
         if len(self.param_groups) != 1:
             raise NotImplementedError("Stoke -- one parameter group (the reference passes model.parameters())")
 

@@ -1,0 +1,121 @@
+"""Worker for the multi-GPU parity tests: launched by tests/test_gpu_multi.py through torch.distributed.run with one
+process per GPU.  Every rank drives the engine with its own seeded gradients; the CPU oracle (W logical ranks) consumes the
+same gradients; rank 0 writes a JSON verdict."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def main(out_path):
+    from engine_oracle import OracleEngine
+    from test_gpu_engine import OddNet, _oracle_flat
+
+    from stoke_b200 import _lib, synthetic
+    from stoke_b200.engine import ClipSpec, get_engine
+    from stoke_b200.optim import B200FusedOptimizer
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = get_engine(local, rank, world)
+    results = {}
+
+    def inject(path, step, r, dtype, scale=1.0):
+        out = []
+        for i, gv in enumerate(path.grad_views):
+            g = synthetic.injected_grad(gv.numel(), r, step * 100 + i, dtype=dtype, scale=scale).view(gv.shape)
+            if r == rank:
+                gv.copy_(g.cuda())
+            out.append(g.float())
+        return out
+
+    cases = [
+        ("ddp_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, False),
+        ("ddp_adam_fp32_accum2", torch.optim.Adam, {"lr": 1e-3, "weight_decay": 0.01}, None, ("norm", 0.5, 2.0), 2, False),
+        ("ddp_sgd_bf16_clipvalue", torch.optim.SGD, {"lr": 0.05, "momentum": 0.9}, torch.bfloat16, ("value", 0.2), 1, False),
+        ("oss_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, True),
+        ("oss_adamw_fp32_accum3_inf", torch.optim.AdamW, {"lr": 1e-3, "weight_decay": 0.05}, None,
+         ("norm", 2.0, float("inf")), 3, True),
+    ]
+    for name, cls, kw, lp, clip, accum, sharded in cases:
+        torch.manual_seed(1234 + rank)  # different init per rank: the engine must broadcast rank 0's
+        net = OddNet(scale=3).cuda()
+        if rank != 0:
+            with torch.no_grad():
+                for p in net.parameters():
+                    p.add_(1.0)
+        spec = ClipSpec(_lib.CLIP_NORM, max_norm=clip[1], norm_type=clip[2]) if clip[0] == "norm" else \
+            ClipSpec(_lib.CLIP_VALUE, clip_value=clip[1])
+        torch.manual_seed(1234)
+        init = [p.detach().cpu().clone() for p in OddNet(scale=3).parameters()]
+        opt = B200FusedOptimizer(net, cls, kw, engine=eng, grad_accum=accum, clip=spec, sharded=sharded, lp_dtype=lp)
+        path = opt.path
+        oracle = OracleEngine(init, world, cls, kw, grad_accum=accum, clip=clip)
+        gdtype = lp or torch.float32
+        for step in range(8):
+            for micro in range(accum):
+                grads = [inject(path, step * accum + micro, r, gdtype) for r in range(world)]
+                oracle.micro_step(grads)
+                path.after_backward(sync=(micro == accum - 1), unscale=False)
+            opt.step()
+            oracle.step()
+        eng.comm_check()
+        ref = _oracle_flat(path, oracle.weights())
+        got = path.gather_master().cpu()
+        err = rel(got, ref)
+        # replicas must be bit-identical: compare this rank's model copy with rank 0's
+        mine = path.p_flat.float().clone()
+        zero = mine.clone()
+        torch.distributed.broadcast(zero, src=0)
+        same = bool(torch.equal(mine, zero))
+        flags = torch.tensor([1.0 if same else 0.0], device="cuda")
+        torch.distributed.all_reduce(flags, op=torch.distributed.ReduceOp.MIN)
+        norm_err = None
+        if clip[0] == "norm":
+            norm_err = abs(eng.scaler_get().grad_norm - float(oracle.last_total_norm)) / float(oracle.last_total_norm)
+        results[name] = {"rel_err": err, "replicas_identical": bool(flags.item() == 1.0), "norm_rel_err": norm_err,
+                         "model_is_rounded_master": bool(torch.equal(path.p_flat.cpu(), got.to(path.model_dtype)))}
+        del opt, path, net
+
+    # loss mean / barrier / inf propagation across ranks
+    t = torch.tensor(float(rank + 1), device="cuda")
+    results["loss_sync"] = eng.loss_sync(t)
+    results["loss_sync_expected"] = sum(range(1, world + 1)) / world
+    eng.barrier()
+
+    from stoke_b200.fp16 import DeviceGradScaler
+    net = OddNet().cuda()
+    opt = B200FusedOptimizer(net, torch.optim.Adam, {"lr": 1e-2}, engine=eng,
+                             clip=ClipSpec(_lib.CLIP_NORM, max_norm=1.0, norm_type=2.0))
+    scaler = DeviceGradScaler(eng, init_scale=2.0**8, growth_interval=1000)
+    before = opt.path.gather_master().clone()
+    inject(opt.path, 0, rank, torch.float32, scale=2.0**8)
+    if rank == world - 1:
+        opt.path.grad_views[0].view(-1)[7] = float("inf")   # only the LAST rank sees the overflow
+    opt.path.after_backward(sync=True, unscale=True)
+    opt.step()
+    st = eng.scaler_get()
+    results["inf_skip"] = {"unchanged": bool(torch.equal(before, opt.path.gather_master())), "scale": st.scale,
+                           "skipped": st.skipped_steps, "steps": st.opt_steps}
+    eng.scaler_set(enabled=0, scale=1.0)
+    eng.comm_check()
+    torch.distributed.barrier()
+    if rank == 0:
+        with open(out_path, "w") as f:
+            json.dump(results, f)
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

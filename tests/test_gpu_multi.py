@@ -1,0 +1,41 @@
+"""Multi-GPU parity (needs >= 2 B200s on the box): K1 all-reduce / reduce-scatter over peer memory, the sharded K2 with
+its in-kernel parameter all-gather, cross-rank norm / inf exchange, loss mean and barrier -- against the CPU oracle with W
+logical ranks.  Each case runs in its own torch.distributed.run job under a hard timeout."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(world, tmp_path, port):
+    out = tmp_path / f"mgpu_{world}.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), str(out)]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-4000:]
+    with open(out) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_parity(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = _run(world, tmp_path, 29500 + world)
+    for name, r in res.items():
+        if not isinstance(r, dict) or "rel_err" not in r:
+            continue
+        assert r["rel_err"] < 1e-5, (name, r)
+        assert r["replicas_identical"], (name, r)
+        assert r["model_is_rounded_master"], (name, r)
+        if r["norm_rel_err"] is not None:
+            assert r["norm_rel_err"] < 1e-5, (name, r)
+    assert res["loss_sync"] == res["loss_sync_expected"]
+    inf = res["inf_skip"]
+    assert inf["unchanged"] and inf["scale"] == 128.0 and inf["skipped"] == 1 and inf["steps"] == 0
