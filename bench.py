@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--oss", action="store_true", help="configs[2]: sharded (ZeRO-1) optimizer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling helper: warm up, then run ONE step between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     return ap.parse_args()
 
 
@@ -188,6 +191,13 @@ def main():
 
     for _ in range(max(3, args.warmup)):
         step_resident()
+    if args.ncu_step:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
 
     # ---- timed region 1: inputs resident; kernel events recorded live for the roofline ----
     eng_events = {"k1": [], "k2": []}

@@ -1,0 +1,154 @@
+# -*- coding: utf-8 -*-
+"""BASELINE.json configs[4]: gradient all-reduce bandwidth sweep, 64 KB - 1 GB bf16 buckets, at W = 2/4/8.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 --master-port P \
+        bench_allreduce.py [--max-mb 1024] [--out gpurun_out/allreduce_W.json]
+
+Per size, device-timed (CUDA events on the launch stream, 10 warm-up + 50 timed back-to-back launches, max over ranks):
+
+  ours_bf16   K1 fused all-reduce, bf16 in -> bf16 out  (+ fused 1/W scale, inf test, sum-of-squares, cross-rank norm
+              exchange): same wire bytes as NCCL, busbw = 2 (W-1)/W S / t
+  ours_fp32   K1 as the training path uses it: bf16 in -> fp32 main grads out (b_out = 4): busbw = (W-1)/W n (2+4) / t
+  nccl        torch.distributed.all_reduce on the same bf16 buffer (the incumbent the reference's DDP path calls)
+  nccl_ddp    all_reduce + _amp_foreach_non_finite_check_and_unscale_ + _foreach_norm (what the reference runs per bucket:
+              stoke/extensions.py:207-215, stoke/fp16.py:180-183, 233)
+  symm_*      torch symmetric-memory two_shot / multimem all-reduce where the build exposes them
+
+Roofline: NVLink 5, 900 GB/s nominal per direction per GPU; measured peer copy on this pool 770 GB/s
+(/opt/skills/guides/B200_PROFILING.md).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def time_op(fn, warmup=10, iters=50):
+    for _ in range(warmup):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--max-mb", type=int, default=1024)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from stoke_b200 import _lib
+    from stoke_b200.engine import get_engine
+
+    eng = get_engine(local, rank, world)
+    sizes = [s for s in (64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20, 1 << 30)
+             if s <= args.max_mb << 20]
+    n_max = max(sizes) // 2
+    G = eng.alloc(n_max * 2)
+    O16 = eng.alloc(n_max * 2)
+    O32 = eng.alloc(n_max * 4)
+    g = G.tensor(torch.bfloat16, n_max)
+    torch.manual_seed(2000 + rank)
+    g.copy_(torch.randn(n_max, device="cuda") * 1e-3)
+
+    symm = None
+    try:
+        import torch.distributed._symmetric_memory as sm
+
+        t_sym = sm.empty(n_max, dtype=torch.bfloat16, device="cuda")
+        sm.rendezvous(t_sym, dist.group.WORLD.group_name)
+        t_sym.zero_()
+        symm = (sm, t_sym, dist.group.WORLD.group_name)
+    except Exception as e:  # noqa: BLE001
+        if rank == 0:
+            print(f"symm_mem unavailable: {type(e).__name__}: {e}", file=sys.stderr)
+
+    rows = []
+    for S in sizes:
+        n = S // 2
+        row = {"bytes": S, "world": world}
+
+        def ours(out_buf, out_dtype):
+            eng.grad_reduce(_lib.REDUCE_ALL, G.peer_ptrs(), torch.bfloat16, None, out_buf.peer_ptrs(), out_dtype, n,
+                            1.0 / world, _lib.NORM_L2, 2.0, _lib.RF_FINAL)
+
+        t = time_op(lambda: ours(O16, torch.bfloat16))
+        row["ours_bf16_us"] = t * 1e3
+        row["ours_bf16_busbw"] = 2 * (world - 1) / world * S / (t * 1e-3) / 1e9
+        t = time_op(lambda: ours(O32, torch.float32))
+        row["ours_fp32_us"] = t * 1e3
+        row["ours_fp32_busbw"] = (world - 1) / world * n * 6 / (t * 1e-3) / 1e9
+
+        buf = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+        t = time_op(lambda: dist.all_reduce(buf))
+        row["nccl_us"] = t * 1e3
+        row["nccl_busbw"] = 2 * (world - 1) / world * S / (t * 1e-3) / 1e9
+        found_inf = torch.zeros(1, device="cuda")
+        inv = torch.ones(1, device="cuda")
+
+        def ddp_like():
+            dist.all_reduce(buf)
+            torch._amp_foreach_non_finite_check_and_unscale_([buf], found_inf, inv)
+            torch._foreach_norm([buf], 2.0)
+
+        t = time_op(ddp_like)
+        row["nccl_ddp_us"] = t * 1e3
+        row["nccl_ddp_busbw"] = 2 * (world - 1) / world * S / (t * 1e-3) / 1e9
+        if symm is not None:
+            sm, t_sym, gname = symm
+            view = t_sym[:n]
+            for name, op in (("symm_two_shot", "two_shot_all_reduce_"), ("symm_multimem", "multimem_all_reduce_"),
+                             ("symm_one_shot", "one_shot_all_reduce")):
+                if name == "symm_one_shot" and S > (4 << 20):
+                    continue
+                try:
+                    fn = getattr(torch.ops.symm_mem, op)
+                    t = time_op(lambda: fn(view, "sum", gname))
+                    row[name + "_us"] = t * 1e3
+                    row[name + "_busbw"] = 2 * (world - 1) / world * S / (t * 1e-3) / 1e9
+                except Exception as e:  # noqa: BLE001
+                    row[name + "_error"] = f"{type(e).__name__}: {str(e)[:120]}"
+        del buf
+        eng.comm_check()
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+    # correctness spot check of the fused kernel on the last size: all ranks hold the same reduced values
+    n = sizes[-1] // 2
+    eng.grad_reduce(_lib.REDUCE_ALL, G.peer_ptrs(), torch.bfloat16, None, O32.peer_ptrs(), torch.float32, n, 1.0 / world,
+                    _lib.NORM_L2, 2.0, _lib.RF_FINAL)
+    mine = O32.tensor(torch.float32, n)[: 1 << 20].clone()
+    ref = g[: 1 << 20].float().clone()
+    dist.all_reduce(ref)
+    ref /= world
+    ok = bool(torch.allclose(mine, ref, rtol=1e-6, atol=1e-9))
+    if rank == 0:
+        summary = {"world": world, "rows": rows, "spot_check_ok": ok,
+                   "nvlink_nominal_gbs": 900, "nvlink_measured_peer_copy_gbs": 770}
+        if args.out:
+            with open(args.out, "w") as f:
+                json.dump(summary, f, indent=1)
+        print("spot check", ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

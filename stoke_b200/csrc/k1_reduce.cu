@@ -268,8 +268,20 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
   }
 }
 
+template <typename K>
+static int resident_blocks(K kernel, int threads, int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * sm_count;
+}
+
 template <int IN_DT, int OUT_DT>
-static cudaError_t launch_reduce(const ReduceParams& p, int grid, bool coop, cudaStream_t s) {
+static cudaError_t launch_reduce(const ReduceParams& p, int grid, int sm_count, bool coop, cudaStream_t s) {
+  if (p.world == 1) {  // local flavour: one full resident wave (no tail wave), capped by the work
+    int res = resident_blocks(k_grad_reduce<IN_DT, OUT_DT, 1>, 512, sm_count);
+    if (res > kMaxBlocks) res = kMaxBlocks;
+    if (grid > res) grid = res;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(512);
@@ -359,11 +371,11 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   size_t want = (nvec_shard + size_t(512) * U - 1) / (size_t(512) * U);
   int grid;
   if (W > 1) grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count));
-  else grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 4));
+  else grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)kMaxBlocks));
   const bool coop = W > 1;
 
   cudaError_t err;
-#define STK_DISPATCH(IN, OUT) err = launch_reduce<IN, OUT>(p, grid, coop, s)
+#define STK_DISPATCH(IN, OUT) err = launch_reduce<IN, OUT>(p, grid, c->sm_count, coop, s)
   if (grad_dtype == STK_BF16 && out_dtype == STK_F32) STK_DISPATCH(STK_BF16, STK_F32);
   else if (grad_dtype == STK_BF16 && out_dtype == STK_BF16) STK_DISPATCH(STK_BF16, STK_BF16);
   else if (grad_dtype == STK_F32 && out_dtype == STK_F32) STK_DISPATCH(STK_F32, STK_F32);

@@ -171,8 +171,15 @@ __global__ void k_step_epilogue(stk_scaler_state_t* st, StepAccum* acc) {
 
 using namespace stk;
 
-template <int KIND>
-static cudaError_t launch_optim(const OptimParams& p, int lp_dtype, int grid, bool coop, cudaStream_t s) {
+template <typename K>
+static cudaError_t launch_one(K kernel, const OptimParams& p, int grid, int sm_count, bool coop, cudaStream_t s) {
+  // one resident wave: grid = min(work, blocks that fit on the chip at once)
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  int res = per_sm * sm_count;
+  if (coop && res > 2 * sm_count) res = 2 * sm_count;
+  if (res > kMaxBlocks) res = kMaxBlocks;
+  if (grid > res) grid = res;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(256);
@@ -182,9 +189,14 @@ static cudaError_t launch_optim(const OptimParams& p, int lp_dtype, int grid, bo
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = coop ? 1 : 0;
-  if (p.lp_world == 0) return cudaLaunchKernelEx(&cfg, k_optim_step<KIND, -1>, p);
-  if (lp_dtype == STK_BF16) return cudaLaunchKernelEx(&cfg, k_optim_step<KIND, STK_BF16>, p);
-  return cudaLaunchKernelEx(&cfg, k_optim_step<KIND, STK_F32>, p);
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
+template <int KIND>
+static cudaError_t launch_optim(const OptimParams& p, int lp_dtype, int grid, int sm_count, bool coop, cudaStream_t s) {
+  if (p.lp_world == 0) return launch_one(k_optim_step<KIND, -1>, p, grid, sm_count, coop, s);
+  if (lp_dtype == STK_BF16) return launch_one(k_optim_step<KIND, STK_BF16>, p, grid, sm_count, coop, s);
+  return launch_one(k_optim_step<KIND, STK_F32>, p, grid, sm_count, coop, s);
 }
 
 extern "C" {
@@ -232,16 +244,13 @@ int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float*
   p.clip_value = (float)h->clip_value;
 
   size_t want = (p.nvec + 511) / 512;  // 256 threads x 2 float4 per iteration
-  int grid;
-  if (p.cross_rank) grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 2));
-  else grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count * 8));
-  if (grid > kMaxBlocks) grid = kMaxBlocks;
+  int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)kMaxBlocks));
 
   cudaError_t err;
   switch (h->kind) {
-    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(p, lp_dtype, grid, p.cross_rank, s); break;
-    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(p, lp_dtype, grid, p.cross_rank, s); break;
-    default: err = launch_optim<STK_OPT_SGD>(p, lp_dtype, grid, p.cross_rank, s); break;
+    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(p, lp_dtype, grid, c->sm_count, p.cross_rank, s); break;
+    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(p, lp_dtype, grid, c->sm_count, p.cross_rank, s); break;
+    default: err = launch_optim<STK_OPT_SGD>(p, lp_dtype, grid, c->sm_count, p.cross_rank, s); break;
   }
   if (err != cudaSuccess) return stk_fail(c, STK_ERR_CUDA, std::string("k_optim_step launch: ") + cudaGetErrorString(err));
   return STK_OK;
