@@ -10,7 +10,7 @@ Per size, device-timed (CUDA events on the launch stream, 10 warm-up + 50 timed 
               exchange): same wire bytes as NCCL, busbw = 2 (W-1)/W S / t
   ours_fp32   K1 as the training path uses it: bf16 in -> fp32 main grads out (b_out = 4): busbw = (W-1)/W n (2+4) / t
   nccl        torch.distributed.all_reduce on the same bf16 buffer (the incumbent the reference's DDP path calls)
-  nccl_ddp    all_reduce + _amp_foreach_non_finite_check_and_unscale_ + _foreach_norm (what the reference runs per bucket:
+  nccl_ddp    all_reduce + cast to fp32 + _amp_foreach_non_finite_check_and_unscale_ + _foreach_norm (what the reference runs per bucket:
               stoke/extensions.py:207-215, stoke/fp16.py:180-183, 233)
   symm_*      torch symmetric-memory two_shot / multimem all-reduce where the build exposes them
 
@@ -105,8 +105,9 @@ def main():
 
         def ddp_like():
             dist.all_reduce(buf)
-            torch._amp_foreach_non_finite_check_and_unscale_([buf], found_inf, inv)
-            torch._foreach_norm([buf], 2.0)
+            f32 = buf.float()  # bf16 grads -> fp32 (the unscale kernel has no bf16 build; the reference's grads are fp32)
+            torch._amp_foreach_non_finite_check_and_unscale_([f32], found_inf, inv)
+            torch._foreach_norm([f32], 2.0)
 
         t = time_op(ddp_like)
         row["nccl_ddp_us"] = t * 1e3

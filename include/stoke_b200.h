@@ -116,6 +116,12 @@ int stk_comm_connect(stk_ctx* ctx, const unsigned char* handles);
 /* copies the device error word to the host (synchronises `stream`); returns STK_ERR_PEER if a spin bound was hit */
 int stk_comm_check(stk_ctx* ctx, void* stream);
 
+/* launch timing for bench.py's roofline: when enabled, K1 (kind 0), K2 (kind 1) and the accumulate kernel (kind 2) are
+ * bracketed by CUDA events on the launch stream; stk_profile_read synchronises those events, returns the summed
+ * duration and the launch count since the last read, and clears the list. */
+int stk_profile_enable(stk_ctx* ctx, int on);
+int stk_profile_read(stk_ctx* ctx, int kind, double* ms_total, int* launches);
+
 /* ---- scaler / step state ------------------------------------------------------------------------------------------- */
 int stk_scaler_set(stk_ctx* ctx, const stk_scaler_state_t* st, void* stream);
 int stk_scaler_get(stk_ctx* ctx, stk_scaler_state_t* st, void* stream); /* synchronises `stream` */

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "stk_comm_local": (C.c_int, [_P, C.c_char_p]),
     "stk_comm_connect": (C.c_int, [_P, C.c_char_p]),
     "stk_comm_check": (C.c_int, [_P, _P]),
+    "stk_profile_enable": (C.c_int, [_P, C.c_int]),
+    "stk_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "stk_scaler_set": (C.c_int, [_P, C.POINTER(ScalerState), _P]),
     "stk_scaler_get": (C.c_int, [_P, C.POINTER(ScalerState), _P]),
     "stk_scaler_scale_ptr": (_P, [_P]),

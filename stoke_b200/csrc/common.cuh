@@ -119,6 +119,24 @@ __device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
   st_stream16(p, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
 }
 
+// 32-byte (256-bit) accesses: sm_100 LDG.E.256 / STG.E.256 -- one warp instruction covers 1 KB contiguous
+struct f8 {
+  float v[8];
+};
+__device__ __forceinline__ f8 ld_stream_f8(const float* p) {
+  f8 r;
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                 "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -244,6 +244,34 @@ int stk_scaler_get(stk_ctx* c, stk_scaler_state_t* st, void* stream) {
 
 void* stk_scaler_scale_ptr(stk_ctx* c) { return c ? static_cast<void*>(&c->scaler_dev->scale) : nullptr; }
 
+int stk_profile_enable(stk_ctx* c, int on) {
+  STK_REQUIRE(c, c != nullptr, "stk_profile_enable: NULL ctx");
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->profiling = on != 0;
+  return STK_OK;
+}
+
+int stk_profile_read(stk_ctx* c, int kind, double* ms_total, int* launches) {
+  STK_REQUIRE(c, c && ms_total && launches && kind >= 0 && kind < 3, "stk_profile_read: bad argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  double tot = 0.0;
+  int n = 0;
+  for (auto& pr : c->prof[kind]) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  c->prof[kind].clear();
+  *ms_total = tot;
+  *launches = n;
+  return STK_OK;
+}
+
 int stk_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end) {
   if (!begin || !end || world < 1 || rank < 0 || rank >= world) return stk_fail(nullptr, STK_ERR_INVALID, "stk_shard_range: bad argument");
   // shards are multiples of 8 elements (16 B of bf16 / 32 B of fp32) so every vector access stays aligned

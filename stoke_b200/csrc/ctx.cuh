@@ -1,6 +1,7 @@
 // ctx.cuh -- host-side context shared by the translation units of libstoke_b200.so
 #pragma once
 #include <map>
+#include <vector>
 #include <mutex>
 #include <string>
 
@@ -35,6 +36,10 @@ struct stk_ctx {
   stk_scaler_state_t* scaler_dev = nullptr;
   StepAccum* accum_dev = nullptr;
   float* blk_partial_dev = nullptr;   // [kMaxBlocks]
+  // optional launch timing (stk_profile_*): CUDA-event pairs recorded around the kernel launch, on the launch stream
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];  // 0: K1 reduce, 1: K2 optimizer step, 2: accumulate
+  std::map<const void*, int> occupancy;                       // kernel -> resident blocks per SM (cached query)
   // pinned, mapped host scratch
   double* host_scratch = nullptr;     // [16]
   double* host_scratch_dev = nullptr; // device alias of host_scratch
@@ -54,6 +59,33 @@ int stk_fail(stk_ctx* ctx, int code, const std::string& msg);
   do {                                                                \
     if (!(cond)) return stk_fail(ctx, STK_ERR_INVALID, (msg));        \
   } while (0)
+
+struct ProfScope {  // records an event pair around a launch when profiling is on
+  stk_ctx* c;
+  int kind;
+  cudaStream_t s;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(stk_ctx* ctx, int k, cudaStream_t st) : c(ctx), kind(k), s(st) {
+    if (c->profiling && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, s);
+  }
+  ~ProfScope() {
+    if (e0 && e1) {
+      cudaEventRecord(e1, s);
+      c->prof[kind].emplace_back(e0, e1);
+    }
+  }
+};
+
+template <typename K>
+static inline int blocks_per_sm(stk_ctx* c, K kernel, int threads) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = c->occupancy.find(key);
+  if (it != c->occupancy.end()) return it->second;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  c->occupancy[key] = per_sm;
+  return per_sm;
+}
 
 struct DeviceGuard {
   int prev = -1;

@@ -41,14 +41,13 @@ template <>
 struct InVec<STK_F32> {
   static constexpr int kBytes = 32;
   __device__ static void load(const void* base, size_t v, float (&f)[8]) {
-    const float* p = reinterpret_cast<const float*>(base) + v * 8;
-    float4 a = ld_stream_f4(p), b = ld_stream_f4(p + 4);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    f8 a = ld_stream_f8(reinterpret_cast<const float*>(base) + v * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = a.v[i];
   }
   __device__ static void zero(void* base, size_t v) {
-    float* p = reinterpret_cast<float*>(base) + v * 8;
-    st_stream16(p, make_uint4(0, 0, 0, 0));
-    st_stream16(p + 4, make_uint4(0, 0, 0, 0));
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    st_stream_f8(reinterpret_cast<float*>(base) + v * 8, z);
   }
 };
 template <>
@@ -79,9 +78,7 @@ struct InVec<STK_F16> {
 template <int DT>
 __device__ __forceinline__ void store_out(void* base, size_t v, const float (&f)[8]) {
   if constexpr (DT == STK_F32) {
-    float* p = reinterpret_cast<float*>(base) + v * 8;
-    st_stream_f4(p, make_float4(f[0], f[1], f[2], f[3]));
-    st_stream_f4(p + 4, make_float4(f[4], f[5], f[6], f[7]));
+    st_stream_f8(reinterpret_cast<float*>(base) + v * 8, f);  // one 32-byte store: full sectors over NVLink
   } else {
     st_stream16(reinterpret_cast<uint4*>(base) + v,
                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
@@ -268,17 +265,10 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
   }
 }
 
-template <typename K>
-static int resident_blocks(K kernel, int threads, int sm_count) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-  return per_sm * sm_count;
-}
-
 template <int IN_DT, int OUT_DT>
-static cudaError_t launch_reduce(const ReduceParams& p, int grid, int sm_count, bool coop, cudaStream_t s) {
+static cudaError_t launch_reduce(stk_ctx* c, const ReduceParams& p, int grid, bool coop, cudaStream_t s) {
   if (p.world == 1) {  // local flavour: one full resident wave (no tail wave), capped by the work
-    int res = resident_blocks(k_grad_reduce<IN_DT, OUT_DT, 1>, 512, sm_count);
+    int res = blocks_per_sm(c, k_grad_reduce<IN_DT, OUT_DT, 1>, 512) * c->sm_count;
     if (res > kMaxBlocks) res = kMaxBlocks;
     if (grid > res) grid = res;
   }
@@ -291,6 +281,7 @@ static cudaError_t launch_reduce(const ReduceParams& p, int grid, int sm_count, 
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = coop ? 1 : 0;
+  ProfScope prof(c, 0, s);
   switch (p.world) {
     case 1: return cudaLaunchKernelEx(&cfg, k_grad_reduce<IN_DT, OUT_DT, 1>, p);
     case 2: return cudaLaunchKernelEx(&cfg, k_grad_reduce<IN_DT, OUT_DT, 2>, p);
@@ -315,6 +306,7 @@ int stk_grad_accumulate(stk_ctx* c, void* grad, int grad_dtype, float* acc, size
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t nvec = n / 8;
   int grid = (int)std::min<size_t>((nvec + 255) / 256, size_t(c->sm_count) * 8);
+  ProfScope prof(c, 2, s);
   switch (grad_dtype) {
     case STK_F32: k_grad_accumulate<STK_F32><<<grid, 256, 0, s>>>(grad, acc, nvec, first, zero_grad); break;
     case STK_BF16: k_grad_accumulate<STK_BF16><<<grid, 256, 0, s>>>(grad, acc, nvec, first, zero_grad); break;
@@ -375,7 +367,7 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   const bool coop = W > 1;
 
   cudaError_t err;
-#define STK_DISPATCH(IN, OUT) err = launch_reduce<IN, OUT>(p, grid, c->sm_count, coop, s)
+#define STK_DISPATCH(IN, OUT) err = launch_reduce<IN, OUT>(c, p, grid, coop, s)
   if (grad_dtype == STK_BF16 && out_dtype == STK_F32) STK_DISPATCH(STK_BF16, STK_F32);
   else if (grad_dtype == STK_BF16 && out_dtype == STK_BF16) STK_DISPATCH(STK_BF16, STK_BF16);
   else if (grad_dtype == STK_F32 && out_dtype == STK_F32) STK_DISPATCH(STK_F32, STK_F32);

@@ -19,7 +19,7 @@ struct OptimParams {
   float* m;
   float* v;
   const float* grad;
-  size_t nvec;          // float4 count
+  size_t nvec;          // 8-float vector count
   PtrTable lp;          // low-precision / remote parameter destinations (already offset)
   int lp_world;         // 0: none
   int lp_rank_skip;     // lp dtype == f32 and destination == master's own buffer: skip that rank (aliased)
@@ -35,21 +35,20 @@ struct OptimParams {
 };
 
 template <int LP_DT>  // -1: none, STK_BF16, STK_F32
-__device__ __forceinline__ void store_lp(const OptimParams& p, size_t i4, const float4& x) {
+__device__ __forceinline__ void store_lp(const OptimParams& p, size_t i8, const float (&x)[8]) {
   if constexpr (LP_DT == STK_BF16) {
-    uint2 u = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+    uint4 u = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
 #pragma unroll 1
     for (int d = 0; d < p.lp_world; ++d) {
       int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
-      uint2* q = reinterpret_cast<uint2*>(p.lp.p[dst]) + i4;
-      asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(q), "r"(u.x), "r"(u.y) : "memory");
+      st_stream16(reinterpret_cast<uint4*>(p.lp.p[dst]) + i8, u);
     }
   } else if constexpr (LP_DT == STK_F32) {
 #pragma unroll 1
     for (int d = 0; d < p.lp_world; ++d) {
       int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
       if (dst == p.lp_rank_skip) continue;
-      st_stream_f4(reinterpret_cast<float*>(p.lp.p[dst]) + i4 * 4, x);
+      st_stream_f8(reinterpret_cast<float*>(p.lp.p[dst]) + i8 * 8, x);
     }
   }
 }
@@ -86,57 +85,46 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
     const float decay_mul = (float)(1.0 - p.lr * p.weight_decay);  // AdamW: param.mul_(1 - lr * wd)
 
     const size_t stride = size_t(gridDim.x) * blockDim.x;
-    constexpr int U = 2;
-    for (size_t i0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < p.nvec; i0 += stride * U) {
-      float4 g[U], w[U], m[U], v[U];
+    const bool use_m = (KIND != STK_OPT_SGD) || mom != 0.f;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < p.nvec; i += stride) {
+      // 4 x 32-byte loads in flight per thread (LDG.E.256)
+      f8 g = ld_stream_f8(p.grad + i * 8);
+      f8 w = ld_stream_f8(p.master + i * 8);
+      f8 m, v;
+      if (use_m) m = ld_stream_f8(p.m + i * 8);
+      if (KIND != STK_OPT_SGD) v = ld_stream_f8(p.v + i * 8);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t i = i0 + u * stride;
-        if (i < p.nvec) {
-          g[u] = ld_stream_f4(p.grad + i * 4);
-          w[u] = ld_stream_f4(p.master + i * 4);
-          if (KIND != STK_OPT_SGD || mom != 0.f) m[u] = ld_stream_f4(p.m + i * 4);
-          if (KIND != STK_OPT_SGD) v[u] = ld_stream_f4(p.v + i * 4);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t i = i0 + u * stride;
-        if (i >= p.nvec) continue;
-        float* gp = &g[u].x; float* wp = &w[u].x; float* mp = &m[u].x; float* vp = &v[u].x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float gg = gp[k];
-          if (p.clip_kind == STK_CLIP_NORM) gg *= coef;
-          else if (p.clip_kind == STK_CLIP_VALUE) gg = fminf(fmaxf(gg, -cv), cv);
-          if (p.maximize) gg = -gg;
-          float ww = wp[k];
-          if (KIND == STK_OPT_ADAM || KIND == STK_OPT_ADAMW) {
-            if (KIND == STK_OPT_ADAMW) ww *= decay_mul;
-            else if (wd != 0.f) gg = fmaf(ww, wd, gg);          // grad.add(param, alpha=wd)
-            float mm = mp[k];
-            mm = fmaf(one_m_b1, gg - mm, mm);                    // exp_avg.lerp_(grad, 1 - beta1)
-            float vv = vp[k] * b2;
-            vv = fmaf(one_m_b2 * gg, gg, vv);                    // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-            float denom = sqrtf(vv) / bc2_sqrt + eps;
-            ww = ww - step_size * (mm / denom);                  // addcdiv_(exp_avg, denom, value=-step_size)
-            mp[k] = mm; vp[k] = vv;
-          } else {  // SGD
-            if (wd != 0.f) gg = fmaf(ww, wd, gg);
-            if (mom != 0.f) {
-              float bb = first_step ? gg : fmaf(mp[k], mom, one_m_damp * gg);
-              mp[k] = bb;
-              gg = p.nesterov ? fmaf(bb, mom, gg) : bb;
-            }
-            ww = fmaf(-lr, gg, ww);
+      for (int k = 0; k < 8; ++k) {
+        float gg = g.v[k];
+        if (p.clip_kind == STK_CLIP_NORM) gg *= coef;
+        else if (p.clip_kind == STK_CLIP_VALUE) gg = fminf(fmaxf(gg, -cv), cv);
+        if (p.maximize) gg = -gg;
+        float ww = w.v[k];
+        if (KIND == STK_OPT_ADAM || KIND == STK_OPT_ADAMW) {
+          if (KIND == STK_OPT_ADAMW) ww *= decay_mul;
+          else if (wd != 0.f) gg = fmaf(ww, wd, gg);          // grad.add(param, alpha=wd)
+          float mm = m.v[k];
+          mm = fmaf(one_m_b1, gg - mm, mm);                    // exp_avg.lerp_(grad, 1 - beta1)
+          float vv = v.v[k] * b2;
+          vv = fmaf(one_m_b2 * gg, gg, vv);                    // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+          float denom = sqrtf(vv) / bc2_sqrt + eps;
+          ww = ww - step_size * (mm / denom);                  // addcdiv_(exp_avg, denom, value=-step_size)
+          m.v[k] = mm; v.v[k] = vv;
+        } else {  // SGD
+          if (wd != 0.f) gg = fmaf(ww, wd, gg);
+          if (mom != 0.f) {
+            float bb = first_step ? gg : fmaf(m.v[k], mom, one_m_damp * gg);
+            m.v[k] = bb;
+            gg = p.nesterov ? fmaf(bb, mom, gg) : bb;
           }
-          wp[k] = ww;
+          ww = fmaf(-lr, gg, ww);
         }
-        st_stream_f4(p.master + i * 4, w[u]);
-        if (KIND != STK_OPT_SGD || mom != 0.f) st_stream_f4(p.m + i * 4, m[u]);
-        if (KIND != STK_OPT_SGD) st_stream_f4(p.v + i * 4, v[u]);
-        store_lp<LP_DT>(p, i, w[u]);
+        w.v[k] = ww;
       }
+      st_stream_f8(p.master + i * 8, w.v);
+      if (use_m) st_stream_f8(p.m + i * 8, m.v);
+      if (KIND != STK_OPT_SGD) st_stream_f8(p.v + i * 8, v.v);
+      store_lp<LP_DT>(p, i, w.v);
     }
   }
   if (p.cross_rank) block_barrier_all_ranks(p.pads, p.rank, p.world, 1, p.epoch);
@@ -172,11 +160,10 @@ __global__ void k_step_epilogue(stk_scaler_state_t* st, StepAccum* acc) {
 using namespace stk;
 
 template <typename K>
-static cudaError_t launch_one(K kernel, const OptimParams& p, int grid, int sm_count, bool coop, cudaStream_t s) {
+static cudaError_t launch_one(stk_ctx* c, K kernel, const OptimParams& p, int grid, bool coop, cudaStream_t s) {
+  const int sm_count = c->sm_count;
   // one resident wave: grid = min(work, blocks that fit on the chip at once)
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-  int res = per_sm * sm_count;
+  int res = blocks_per_sm(c, kernel, 256) * sm_count;
   if (coop && res > 2 * sm_count) res = 2 * sm_count;
   if (res > kMaxBlocks) res = kMaxBlocks;
   if (grid > res) grid = res;
@@ -189,14 +176,15 @@ static cudaError_t launch_one(K kernel, const OptimParams& p, int grid, int sm_c
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = coop ? 1 : 0;
+  ProfScope prof(c, 1, s);
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 template <int KIND>
-static cudaError_t launch_optim(const OptimParams& p, int lp_dtype, int grid, int sm_count, bool coop, cudaStream_t s) {
-  if (p.lp_world == 0) return launch_one(k_optim_step<KIND, -1>, p, grid, sm_count, coop, s);
-  if (lp_dtype == STK_BF16) return launch_one(k_optim_step<KIND, STK_BF16>, p, grid, sm_count, coop, s);
-  return launch_one(k_optim_step<KIND, STK_F32>, p, grid, sm_count, coop, s);
+static cudaError_t launch_optim(stk_ctx* c, const OptimParams& p, int lp_dtype, int grid, bool coop, cudaStream_t s) {
+  if (p.lp_world == 0) return launch_one(c, k_optim_step<KIND, -1>, p, grid, coop, s);
+  if (lp_dtype == STK_BF16) return launch_one(c, k_optim_step<KIND, STK_BF16>, p, grid, coop, s);
+  return launch_one(c, k_optim_step<KIND, STK_F32>, p, grid, coop, s);
 }
 
 extern "C" {
@@ -205,7 +193,7 @@ int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float*
                    const float* grad, size_t n_local, void* const* lp_ptrs, int lp_world, int lp_dtype, size_t lp_offset,
                    void* stream) {
   STK_REQUIRE(c, c && h && master && grad, "stk_optim_step: NULL argument");
-  STK_REQUIRE(c, n_local % 4 == 0, "stk_optim_step: n_local must be a multiple of 4");
+  STK_REQUIRE(c, n_local % 8 == 0, "stk_optim_step: n_local must be a multiple of 8");
   STK_REQUIRE(c, h->kind >= STK_OPT_ADAM && h->kind <= STK_OPT_SGD, "stk_optim_step: bad optimizer kind");
   STK_REQUIRE(c, h->kind == STK_OPT_SGD || (exp_avg && exp_avg_sq), "stk_optim_step: Adam needs exp_avg and exp_avg_sq");
   STK_REQUIRE(c, !(h->kind == STK_OPT_SGD && h->momentum != 0.0 && !exp_avg), "stk_optim_step: SGD momentum needs a buffer");
@@ -221,7 +209,7 @@ int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float*
   p.m = exp_avg;
   p.v = exp_avg_sq;
   p.grad = grad;
-  p.nvec = n_local / 4;
+  p.nvec = n_local / 8;
   p.lp_world = lp_ptrs ? lp_world : 0;
   p.lp_rank_skip = -1;
   const size_t esz = lp_dtype == STK_BF16 ? 2 : 4;
@@ -243,14 +231,14 @@ int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float*
   p.clip_max_norm = (float)h->clip_max_norm;
   p.clip_value = (float)h->clip_value;
 
-  size_t want = (p.nvec + 511) / 512;  // 256 threads x 2 float4 per iteration
+  size_t want = (p.nvec + 255) / 256;  // 256 threads x one 8-float vector per iteration
   int grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)kMaxBlocks));
 
   cudaError_t err;
   switch (h->kind) {
-    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(p, lp_dtype, grid, c->sm_count, p.cross_rank, s); break;
-    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(p, lp_dtype, grid, c->sm_count, p.cross_rank, s); break;
-    default: err = launch_optim<STK_OPT_SGD>(p, lp_dtype, grid, c->sm_count, p.cross_rank, s); break;
+    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(c, p, lp_dtype, grid, p.cross_rank, s); break;
+    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(c, p, lp_dtype, grid, p.cross_rank, s); break;
+    default: err = launch_optim<STK_OPT_SGD>(c, p, lp_dtype, grid, p.cross_rank, s); break;
   }
   if (err != cudaSuccess) return stk_fail(c, STK_ERR_CUDA, std::string("k_optim_step launch: ") + cudaGetErrorString(err));
   return STK_OK;

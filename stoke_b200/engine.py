@@ -174,6 +174,16 @@ class Engine:
         self._check(self.lib.stk_bcast(self.ctx, _lib.ptr_array(buf.peer_ptrs(offset_bytes)), nbytes, root, self._stream()))
         self.launches += 1
 
+    def profile(self, on: bool):
+        """Brackets K1 / K2 / accumulate launches with CUDA events inside the library (for bench.py's roofline)."""
+        self._check(self.lib.stk_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self, kind: int):
+        """(total ms, launches) since the last read for kind 0 = K1, 1 = K2, 2 = accumulate."""
+        ms, n = C.c_double(), C.c_int()
+        self._check(self.lib.stk_profile_read(self.ctx, kind, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def comm_check(self):
         self._check(self.lib.stk_comm_check(self.ctx, self._stream()))
 
