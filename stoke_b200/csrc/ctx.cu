@@ -54,6 +54,7 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   cudaMemcpy(c->scaler_dev, &st, sizeof(st), cudaMemcpyHostToDevice);
   cudaMemset(c->accum_dev, 0, sizeof(StepAccum));
   cudaMemset(c->blk_partial_dev, 0, sizeof(float) * stk::kMaxBlocks);
+  c->blk_partial_cap = stk::kMaxBlocks;
   for (int i = 0; i < STK_MAX_WORLD; ++i) c->pads.p[i] = nullptr;
   *out = c;
   return STK_OK;

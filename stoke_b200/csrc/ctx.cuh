@@ -35,7 +35,8 @@ struct stk_ctx {
   // device state
   stk_scaler_state_t* scaler_dev = nullptr;
   StepAccum* accum_dev = nullptr;
-  float* blk_partial_dev = nullptr;   // [kMaxBlocks]
+  float* blk_partial_dev = nullptr;   // [blk_partial_cap]
+  size_t blk_partial_cap = 0;
   // optional launch timing (stk_profile_*): CUDA-event pairs recorded around the kernel launch, on the launch stream
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];  // 0: K1 reduce, 1: K2 optimizer step, 2: accumulate

@@ -89,8 +89,10 @@ __device__ __forceinline__ void store_out(void* base, size_t v, const float (&f)
 template <int IN_DT>
 __global__ void __launch_bounds__(256) k_grad_accumulate(void* __restrict__ grad, float* __restrict__ acc, size_t nvec,
                                                          int first, int zero_grad) {
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+  // one vector per thread, one block per chunk: measured 10-15% faster than a persistent grid-stride loop on B200
+  // (tools/membench.cu; profiles/membench_r01.md)
+  const size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v < nvec) {
     float g[8];
     InVec<IN_DT>::load(grad, v, g);
     if (!first) {
@@ -114,7 +116,7 @@ struct Unroll {
 template <int IN_DT, int OUT_DT, int W_T>
 __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
   __shared__ float s_red[32];
-  __shared__ int s_last;
+  __shared__ unsigned s_bad[32];
   const int W = W_T ? W_T : p.world;
   constexpr int U = Unroll<W_T>::value;
   constexpr int WMAX = W_T ? W_T : kMaxWorld;
@@ -130,8 +132,13 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
   float part = 0.f;   // norm partial of this thread
   bool bad = false;   // saw inf/nan
 
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t v0 = p.vec_begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x; v0 < p.vec_end; v0 += stride * U) {
+  // W == 1 (local, HBM-bound): one-shot launch, each block owns U * blockDim contiguous vectors (no grid-stride loop:
+  // 10-15% faster on B200, tools/membench.cu).  W > 1 (NVLink-bound, blocks spin on peers): persistent grid-stride.
+  const size_t stride = (W_T == 1) ? size_t(blockDim.x) : size_t(gridDim.x) * blockDim.x;
+  const size_t first = (W_T == 1) ? p.vec_begin + size_t(blockIdx.x) * blockDim.x * U + threadIdx.x
+                                  : p.vec_begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t step = (W_T == 1) ? ~size_t(0) / 2 : stride * U;
+  for (size_t v0 = first; v0 < p.vec_end; v0 += step) {
     float g[U][WMAX][8];
     float a[U][8];
     // issue every load before the first use (latency over NVLink is ~2 us)
@@ -192,34 +199,60 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
     }
   }
 
-  // ---- per-block partials (fixed tree: run-to-run deterministic) ----
-  if (p.norm_kind != STK_NORM_NONE) {
-    float blk = (p.norm_kind == STK_NORM_INF) ? block_reduce<true>(part, s_red) : block_reduce<false>(part, s_red);
-    if (threadIdx.x == 0) p.blk_partial[blockIdx.x] = blk;
+  // ---- per-block partials (fixed tree: run-to-run deterministic); ONE block-wide barrier, then only warp 0 continues ----
+  {
+    const bool mx = p.norm_kind == STK_NORM_INF;
+    const float wsum = mx ? warp_reduce<true>(part) : warp_reduce<false>(part);
+    const unsigned wbad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      s_red[threadIdx.x >> 5] = wsum;
+      s_bad[threadIdx.x >> 5] = wbad;
+    }
   }
-  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(&p.accum->found_inf, 1u);
+  __syncthreads();
 
   if (W > 1) block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch);
 
-  // ---- last block of this rank: fold the bucket into the step accumulators; on FINAL exchange across ranks ----
-  if (threadIdx.x == 0) {
+  // Only warp 0 stays for the bookkeeping: the other warps retire now, so a block never sits idle on the ticket's
+  // fence + atomic round trip (that idle time cost ~40% at W == 1, where thousands of one-shot blocks pass through here).
+  if (threadIdx.x >= 32) return;
+  const unsigned lane = threadIdx.x;
+  const unsigned nwarp = (blockDim.x + 31) >> 5;
+  float blk = lane < nwarp ? s_red[lane] : 0.f;
+  blk = (p.norm_kind == STK_NORM_INF) ? warp_reduce<true>(blk) : warp_reduce<false>(blk);
+  const unsigned any_bad = __any_sync(0xffffffffu, lane < nwarp && s_bad[lane] != 0);
+  unsigned last = 0;
+  if (lane == 0) {
+    if (p.norm_kind != STK_NORM_NONE) p.blk_partial[blockIdx.x] = blk;
+    if (any_bad) atomicOr(&p.accum->found_inf, 1u);
     __threadfence();
-    unsigned t = atomicAdd(&p.accum->blocks_done, 1u);
-    s_last = (t == gridDim.x - 1);
+    const unsigned t = atomicAdd(&p.accum->blocks_done, 1u);
+    last = (t == gridDim.x - 1);
   }
-  __syncthreads();
-  if (!s_last) return;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+
+  // ---- last block of this rank: fold the bucket into the step accumulators; on FINAL exchange across ranks ----
   __threadfence();
   float tot = 0.f;
   if (p.norm_kind != STK_NORM_NONE) {
+    const bool mx = p.norm_kind == STK_NORM_INF;
     float x = 0.f;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-      float y = __ldcg(&p.blk_partial[i]);
-      x = (p.norm_kind == STK_NORM_INF) ? fmaxf(x, y) : x + y;
+    const unsigned n4 = gridDim.x / 4;
+    const float4* p4 = reinterpret_cast<const float4*>(p.blk_partial);
+#pragma unroll 4
+    for (unsigned i = lane; i < n4; i += 32) {  // fixed lane/iteration order -> deterministic
+      const float4 y = __ldcg(p4 + i);
+      x = mx ? fmaxf(fmaxf(fmaxf(fmaxf(x, y.x), y.y), y.z), y.w) : (((x + y.x) + y.y) + y.z) + y.w;
     }
-    tot = (p.norm_kind == STK_NORM_INF) ? block_reduce<true>(x, s_red) : block_reduce<false>(x, s_red);
+    if (lane == 0)
+      for (unsigned i = n4 * 4; i < gridDim.x; ++i) {
+        const float y = __ldcg(&p.blk_partial[i]);
+        x = mx ? fmaxf(x, y) : x + y;
+      }
+    tot = mx ? warp_reduce<true>(x) : warp_reduce<false>(x);
   }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     float run = p.accum->norm_partial;
     run = (p.norm_kind == STK_NORM_INF) ? fmaxf(run, tot) : run + tot;
     p.accum->norm_partial = run;
@@ -227,20 +260,20 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
     __threadfence();
   }
   if (!(p.flags & STK_RF_FINAL)) return;
-  __syncthreads();
+  __syncwarp();
   if (W > 1) {
-    if (threadIdx.x < (unsigned)W) {
-      const int peer = threadIdx.x;
+    if (lane < (unsigned)W) {
+      const int peer = lane;
       RankScalars* slot = &p.pads.p[peer]->scal[p.rank];
-      st_relaxed_sys_f32(&slot->norm_partial, p.accum->norm_partial);
+      st_relaxed_sys_f32(&slot->norm_partial, __ldcg(&p.accum->norm_partial));
       st_relaxed_sys_u32(&slot->found_inf, atomicOr(&p.accum->found_inf, 0u));
       __threadfence_system();
       st_release_sys(&p.pads.p[peer]->aux_flag[0][p.rank], p.aux_epoch);
       wait_flag(&p.pads.p[p.rank]->aux_flag[0][peer], p.aux_epoch, &p.pads.p[p.rank]->error);
     }
-    __syncthreads();
+    __syncwarp();
   }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     float total = 0.f;
     uint32_t inf = 0;
     if (W > 1) {
@@ -267,14 +300,9 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
 
 template <int IN_DT, int OUT_DT>
 static cudaError_t launch_reduce(stk_ctx* c, const ReduceParams& p, int grid, bool coop, cudaStream_t s) {
-  if (p.world == 1) {  // local flavour: one full resident wave (no tail wave), capped by the work
-    int res = blocks_per_sm(c, k_grad_reduce<IN_DT, OUT_DT, 1>, 512) * c->sm_count;
-    if (res > kMaxBlocks) res = kMaxBlocks;
-    if (grid > res) grid = res;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(512);
+  cfg.blockDim = dim3(p.world == 1 ? 256 : 512);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
@@ -305,7 +333,7 @@ int stk_grad_accumulate(stk_ctx* c, void* grad, int grad_dtype, float* acc, size
   DeviceGuard g(c->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t nvec = n / 8;
-  int grid = (int)std::min<size_t>((nvec + 255) / 256, size_t(c->sm_count) * 8);
+  const unsigned grid = (unsigned)((nvec + 255) / 256);
   ProfScope prof(c, 2, s);
   switch (grad_dtype) {
     case STK_F32: k_grad_accumulate<STK_F32><<<grid, 256, 0, s>>>(grad, acc, nvec, first, zero_grad); break;
@@ -360,10 +388,20 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   // resident: one 512-thread block per SM, cooperative launch.
   const size_t nvec_shard = ((n + 7) / 8 + W - 1) / W;
   const int U = W == 1 ? 4 : (W == 2 ? 2 : 1);
-  size_t want = (nvec_shard + size_t(512) * U - 1) / (size_t(512) * U);
+  const size_t threads = W == 1 ? 256 : 512;
+  size_t want = (nvec_shard + threads * U - 1) / (threads * U);
   int grid;
   if (W > 1) grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count));
-  else grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)kMaxBlocks));
+  else grid = (int)std::max<size_t>(1, want);  // one-shot: every block does one chunk
+  if ((size_t)grid > c->blk_partial_cap) {     // per-block norm partials (summed in fixed order by the last block)
+    float* np = nullptr;
+    STK_CUDA(c, cudaMalloc(&np, sizeof(float) * (size_t)grid));
+    STK_CUDA(c, cudaStreamSynchronize(s));
+    cudaFree(c->blk_partial_dev);
+    c->blk_partial_dev = np;
+    c->blk_partial_cap = (size_t)grid;
+    p.blk_partial = np;
+  }
   const bool coop = W > 1;
 
   cudaError_t err;
