@@ -11,6 +11,28 @@ int stk_fail(stk_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
+int stk_grow_partials(stk_ctx* c, size_t blocks, cudaStream_t s) {
+  if (blocks <= c->blk_partial_cap) return STK_OK;
+  const size_t groups = blocks / 64 + 1;
+  float *bp = nullptr, *gp = nullptr;
+  uint32_t* gc = nullptr;
+  STK_CUDA(c, cudaMalloc(&bp, sizeof(float) * blocks));
+  STK_CUDA(c, cudaMalloc(&gp, sizeof(float) * groups));
+  STK_CUDA(c, cudaMalloc(&gc, sizeof(uint32_t) * groups));
+  STK_CUDA(c, cudaMemset(gc, 0, sizeof(uint32_t) * groups));
+  if (c->blk_partial_dev) {
+    STK_CUDA(c, cudaStreamSynchronize(s));  // a previous launch may still use the old arrays
+    cudaFree(c->blk_partial_dev);
+    cudaFree(c->grp_partial_dev);
+    cudaFree(c->grp_count_dev);
+  }
+  c->blk_partial_dev = bp;
+  c->grp_partial_dev = gp;
+  c->grp_count_dev = gc;
+  c->blk_partial_cap = blocks;
+  return STK_OK;
+}
+
 extern "C" {
 
 int stk_version(void) { return 100; }
@@ -40,7 +62,6 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   cudaError_t e;
   if ((e = cudaMalloc(&c->scaler_dev, sizeof(stk_scaler_state_t))) != cudaSuccess ||
       (e = cudaMalloc(&c->accum_dev, sizeof(StepAccum))) != cudaSuccess ||
-      (e = cudaMalloc(&c->blk_partial_dev, sizeof(float) * stk::kMaxBlocks)) != cudaSuccess ||
       (e = cudaHostAlloc(&c->host_scratch, sizeof(double) * 16, cudaHostAllocMapped)) != cudaSuccess ||
       (e = cudaHostGetDevicePointer(&c->host_scratch_dev, c->host_scratch, 0)) != cudaSuccess) {
     delete c;
@@ -53,8 +74,10 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   st.growth_interval = 2000;
   cudaMemcpy(c->scaler_dev, &st, sizeof(st), cudaMemcpyHostToDevice);
   cudaMemset(c->accum_dev, 0, sizeof(StepAccum));
-  cudaMemset(c->blk_partial_dev, 0, sizeof(float) * stk::kMaxBlocks);
-  c->blk_partial_cap = stk::kMaxBlocks;
+  if (stk_grow_partials(c, stk::kMaxBlocks, nullptr) != STK_OK) {
+    delete c;
+    return STK_ERR_CUDA;
+  }
   for (int i = 0; i < STK_MAX_WORLD; ++i) c->pads.p[i] = nullptr;
   *out = c;
   return STK_OK;
@@ -77,6 +100,8 @@ int stk_ctx_destroy(stk_ctx* c) {
   cudaFree(c->scaler_dev);
   cudaFree(c->accum_dev);
   cudaFree(c->blk_partial_dev);
+  cudaFree(c->grp_partial_dev);
+  cudaFree(c->grp_count_dev);
   cudaFreeHost(c->host_scratch);
   delete c;
   return STK_OK;

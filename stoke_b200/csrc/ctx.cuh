@@ -35,7 +35,9 @@ struct stk_ctx {
   // device state
   stk_scaler_state_t* scaler_dev = nullptr;
   StepAccum* accum_dev = nullptr;
-  float* blk_partial_dev = nullptr;   // [blk_partial_cap]
+  float* blk_partial_dev = nullptr;   // [blk_partial_cap] per-block norm partials of K1
+  float* grp_partial_dev = nullptr;   // [blk_partial_cap / 64 + 1] per-group partials (two-level ticket)
+  uint32_t* grp_count_dev = nullptr;  // [blk_partial_cap / 64 + 1] group tickets (self-resetting)
   size_t blk_partial_cap = 0;
   // optional launch timing (stk_profile_*): CUDA-event pairs recorded around the kernel launch, on the launch stream
   bool profiling = false;
@@ -60,6 +62,8 @@ int stk_fail(stk_ctx* ctx, int code, const std::string& msg);
   do {                                                                \
     if (!(cond)) return stk_fail(ctx, STK_ERR_INVALID, (msg));        \
   } while (0)
+
+int stk_grow_partials(stk_ctx* c, size_t blocks, cudaStream_t s);
 
 struct ProfScope {  // records an event pair around a launch when profiling is on
   stk_ctx* c;

@@ -25,7 +25,9 @@ struct ReduceParams {
   PeerPads pads;
   stk_scaler_state_t* scaler;
   StepAccum* accum;
-  float* blk_partial;
+  float* blk_partial;   // [grid] per-block norm partials
+  float* grp_partial;   // [grid / 64 + 1] per-group partials
+  uint32_t* grp_count;  // [grid / 64 + 1] group tickets
   size_t vec_begin, vec_end;  // owned shard in units of 8 elements
   float mul;
   float norm_p;
@@ -221,35 +223,49 @@ __global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
   float blk = lane < nwarp ? s_red[lane] : 0.f;
   blk = (p.norm_kind == STK_NORM_INF) ? warp_reduce<true>(blk) : warp_reduce<false>(blk);
   const unsigned any_bad = __any_sync(0xffffffffu, lane < nwarp && s_bad[lane] != 0);
+  // Two-level ticket (groups of 64 blocks): the last block of a group folds the group's partials, the last group folds
+  // the group partials -- fixed order at both levels (deterministic), and the serial tail stays short even with the tens
+  // of thousands of one-shot blocks of a W == 1 launch.
+  const bool mx = p.norm_kind == STK_NORM_INF;
+  const unsigned grp = blockIdx.x >> 6, ngroups = (gridDim.x + 63) >> 6;
+  const unsigned gsize = min(64u, gridDim.x - (grp << 6));
   unsigned last = 0;
   if (lane == 0) {
     if (p.norm_kind != STK_NORM_NONE) p.blk_partial[blockIdx.x] = blk;
     if (any_bad) atomicOr(&p.accum->found_inf, 1u);
     __threadfence();
-    const unsigned t = atomicAdd(&p.accum->blocks_done, 1u);
-    last = (t == gridDim.x - 1);
+    last = (atomicAdd(&p.grp_count[grp], 1u) == gsize - 1);
   }
   last = __shfl_sync(0xffffffffu, last, 0);
   if (!last) return;
+  __threadfence();
+  {
+    float x = 0.f;
+    if (p.norm_kind != STK_NORM_NONE) {
+      const float a = lane < gsize ? __ldcg(&p.blk_partial[(grp << 6) + lane]) : 0.f;
+      const float b = lane + 32 < gsize ? __ldcg(&p.blk_partial[(grp << 6) + 32 + lane]) : 0.f;
+      x = mx ? warp_reduce<true>(fmaxf(a, b)) : warp_reduce<false>(a + b);
+    }
+    last = 0;
+    if (lane == 0) {
+      p.grp_partial[grp] = x;
+      p.grp_count[grp] = 0;
+      __threadfence();
+      last = (atomicAdd(&p.accum->blocks_done, 1u) == ngroups - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+  }
 
-  // ---- last block of this rank: fold the bucket into the step accumulators; on FINAL exchange across ranks ----
+  // ---- last group of this rank: fold the bucket into the step accumulators; on FINAL exchange across ranks ----
   __threadfence();
   float tot = 0.f;
   if (p.norm_kind != STK_NORM_NONE) {
-    const bool mx = p.norm_kind == STK_NORM_INF;
     float x = 0.f;
-    const unsigned n4 = gridDim.x / 4;
-    const float4* p4 = reinterpret_cast<const float4*>(p.blk_partial);
-#pragma unroll 4
-    for (unsigned i = lane; i < n4; i += 32) {  // fixed lane/iteration order -> deterministic
-      const float4 y = __ldcg(p4 + i);
-      x = mx ? fmaxf(fmaxf(fmaxf(fmaxf(x, y.x), y.y), y.z), y.w) : (((x + y.x) + y.y) + y.z) + y.w;
+    for (unsigned i = lane; i < ngroups; i += 32) {  // fixed lane/iteration order -> deterministic
+      const float y = __ldcg(&p.grp_partial[i]);
+      x = mx ? fmaxf(x, y) : x + y;
     }
-    if (lane == 0)
-      for (unsigned i = n4 * 4; i < gridDim.x; ++i) {
-        const float y = __ldcg(&p.blk_partial[i]);
-        x = mx ? fmaxf(x, y) : x + y;
-      }
     tot = mx ? warp_reduce<true>(x) : warp_reduce<false>(x);
   }
   if (lane == 0) {
@@ -370,6 +386,8 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   p.scaler = c->scaler_dev;
   p.accum = c->accum_dev;
   p.blk_partial = c->blk_partial_dev;
+  p.grp_partial = c->grp_partial_dev;
+  p.grp_count = c->grp_count_dev;
   size_t b = 0, e = 0;
   stk_shard_range(n, W, c->rank, &b, &e);
   p.vec_begin = b / 8;
@@ -393,14 +411,12 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   int grid;
   if (W > 1) grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count));
   else grid = (int)std::max<size_t>(1, want);  // one-shot: every block does one chunk
-  if ((size_t)grid > c->blk_partial_cap) {     // per-block norm partials (summed in fixed order by the last block)
-    float* np = nullptr;
-    STK_CUDA(c, cudaMalloc(&np, sizeof(float) * (size_t)grid));
-    STK_CUDA(c, cudaStreamSynchronize(s));
-    cudaFree(c->blk_partial_dev);
-    c->blk_partial_dev = np;
-    c->blk_partial_cap = (size_t)grid;
-    p.blk_partial = np;
+  {
+    int rc = stk_grow_partials(c, (size_t)grid, s);
+    if (rc != STK_OK) return rc;
+    p.blk_partial = c->blk_partial_dev;
+    p.grp_partial = c->grp_partial_dev;
+    p.grp_count = c->grp_count_dev;
   }
   const bool coop = W > 1;
 
