@@ -111,12 +111,12 @@ __global__ void __launch_bounds__(256) k_grad_accumulate(void* __restrict__ grad
 // ---------------------------------------------------------------------------------------------------------------------
 template <int W>
 struct Unroll {
-  static constexpr int value = W == 1 ? 4 : (W == 2 ? 2 : 1);
+  static constexpr int value = W == 1 ? 2 : (W == 2 ? 2 : 1);
 };
 
 // W_T: compile-time world size (1, 2, 4, 8) or 0 = runtime p.world
 template <int IN_DT, int OUT_DT, int W_T>
-__global__ void __launch_bounds__(512) k_grad_reduce(const ReduceParams p) {
+__global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad_reduce(const ReduceParams p) {
   __shared__ float s_red[32];
   __shared__ unsigned s_bad[32];
   const int W = W_T ? W_T : p.world;
@@ -405,7 +405,7 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   // grid: identical on every rank (depends on n and W only).  Cross-rank kernels spin on peers, so every block must be
   // resident: one 512-thread block per SM, cooperative launch.
   const size_t nvec_shard = ((n + 7) / 8 + W - 1) / W;
-  const int U = W == 1 ? 4 : (W == 2 ? 2 : 1);
+  const int U = W == 1 ? 2 : (W == 2 ? 2 : 1);
   const size_t threads = W == 1 ? 256 : 512;
   size_t want = (nvec_shard + threads * U - 1) / (threads * U);
   int grid;

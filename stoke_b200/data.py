@@ -37,7 +37,7 @@ def argsort_lengths(lengths, device: Optional[int] = None) -> torch.Tensor:
     """Stable argsort of non-negative integer lengths on the device (LSD radix sort); returns int64 indices (CUDA)."""
     eng = get_engine(device)
     dev = torch.device("cuda", eng.device)
-    keys = torch.as_tensor(np.asarray(lengths)).to(dev)
+    keys = lengths.to(dev) if isinstance(lengths, torch.Tensor) else torch.as_tensor(np.asarray(lengths)).to(dev)
     if keys.numel() == 0:
         return torch.empty(0, dtype=torch.int64, device=dev)
     if keys.dtype not in (torch.int32, torch.int64, torch.uint8, torch.int16) or int(keys.min()) < 0 \
