@@ -22,6 +22,47 @@ from .engine import get_engine
 from .utils import place_data_on_gpu
 
 
+class DevicePrefetcher:
+    """Wraps an iterator of host batches: batch i+1 is copied to the GPU on a side stream while batch i is being consumed
+    (the reference's ``place_data_on_gpu`` is a blocking ``.to("cuda")`` per tensor, stoke/utils.py:39-80).  Copies overlap
+    compute when the host tensors are pinned (``DataLoader(pin_memory=True)``)."""
+
+    def __init__(self, host_iter, fp16=None, device=None):
+        self._it = iter(host_iter)
+        self._fp16 = fp16
+        self._device = torch.cuda.current_device() if device is None else device
+        self._stream = torch.cuda.Stream(self._device)
+
+    def _stage(self):
+        try:
+            batch = next(self._it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self._stream):
+            return place_data_on_gpu(batch, self._fp16)
+
+    @staticmethod
+    def _record(batch, stream):
+        if isinstance(batch, torch.Tensor):
+            batch.record_stream(stream)
+        elif isinstance(batch, (list, tuple)):
+            for b in batch:
+                DevicePrefetcher._record(b, stream)
+        elif isinstance(batch, dict):
+            for b in batch.values():
+                DevicePrefetcher._record(b, stream)
+
+    def __iter__(self):
+        nxt = self._stage()
+        while nxt is not None:
+            cur_stream = torch.cuda.current_stream(self._device)
+            cur_stream.wait_stream(self._stream)
+            cur = nxt
+            self._record(cur, cur_stream)
+            nxt = self._stage()
+            yield cur
+
+
 class StokeDataLoader(DL):
     def __init__(self, dataset, gpu: bool, fp16=None, **kwargs):
         super().__init__(dataset, **kwargs)
@@ -29,8 +70,10 @@ class StokeDataLoader(DL):
         self._fp16 = fp16
 
     def __iter__(self):
-        for val in super().__iter__():
-            yield val if not self._gpu else place_data_on_gpu(val, self._fp16)
+        if not self._gpu:
+            yield from super().__iter__()
+        else:
+            yield from DevicePrefetcher(super().__iter__(), self._fp16)
 
 
 def argsort_lengths(lengths, device: Optional[int] = None) -> torch.Tensor:

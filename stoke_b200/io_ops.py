@@ -32,7 +32,8 @@ class BaseStokeIO:
             self._print_device(f"Attempting to save model checkpoint to {full}")
         self.barrier()
         optimizer_dict = optimizer.state_dict()  # collective when the state is sharded: every rank calls it
-        model_dict = model.state_dict()
+        # parameters / buffers are typed views of the engine's flat buffers: detach them into ordinary per-tensor storages
+        model_dict = {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in model.state_dict().items()}
         if self._is_writer():
             try:
                 if create_directory:

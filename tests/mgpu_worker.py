@@ -110,11 +110,89 @@ def main(out_path):
                            "skipped": st.skipped_steps, "steps": st.opt_steps}
     eng.scaler_set(enabled=0, scale=1.0)
     eng.comm_check()
+    results["stoke_api"] = stoke_api_section(rank, world, local, os.path.dirname(out_path))
+    eng.comm_check()
     torch.distributed.barrier()
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump(results, f)
     torch.distributed.destroy_process_group()
+
+
+def stoke_api_section(rank, world, local, tmpdir):
+    """The public API under DDP / OSS / SDDP on real GPUs: replicas stay bit-identical, BatchNorm buffers follow rank 0
+    (broadcast_buffers), the synced loss is the mean over ranks, and save -> load -> continue reproduces the uninterrupted run."""
+    import stoke_b200 as sb
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(21)
+            self.fc1 = torch.nn.Linear(64, 96)
+            self.bn = torch.nn.BatchNorm1d(96)
+            self.fc2 = torch.nn.Linear(96, 1)
+            with torch.no_grad():
+                for p in self.parameters():
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+
+        def forward(self, x):
+            return self.fc2(torch.relu(self.bn(self.fc1(x))))
+
+    def batch(step, r):
+        g = torch.Generator().manual_seed(77 * step + r)
+        return torch.randn(32, 64, generator=g).cuda(), (torch.rand(32, 1, generator=g) > 0.5).float().cuda()
+
+    def all_equal(t):
+        ref = t.clone()
+        torch.distributed.broadcast(ref, src=0)
+        flag = torch.tensor([1.0 if torch.equal(ref, t) else 0.0], device="cuda")
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        return bool(flag.item() == 1.0)
+
+    out = {}
+    for name, flags in (("ddp", {}), ("oss", {"fairscale_oss": True}), ("oss_sddp", {"fairscale_oss": True, "fairscale_sddp": True})):
+        def make():
+            return sb.Stoke(model=Net(), optimizer=sb.StokeOptimizer(optimizer=torch.optim.AdamW, optimizer_kwargs={"lr": 2e-3}),
+                            loss=torch.nn.BCEWithLogitsLoss(), batch_size_per_device=32, grad_accum_steps=2,
+                            grad_clip=sb.ClipGradNormConfig(max_norm=0.5, norm_type=2.0), gpu=True, fp16="bf16",
+                            distributed="ddp", configs=[sb.DDPConfig(local_rank=local)], verbose=False, **flags)
+
+        def run(s, steps):
+            synced = []
+            for st in steps:
+                x, y = batch(st, rank)
+                s.backward(s.loss(s.model(x), y))
+                synced.append(s.step_loss)
+                s.step()
+            return synced
+
+        a = make()
+        la = run(a, range(0, 6))
+        path, tag = a.save(tmpdir, name=f"ck_{name}")
+        la += run(a, range(6, 12))
+        wa = a.optimizer.path.gather_master().clone()
+        # like torch DDP, rank 0's buffers are broadcast at the START of a forward; ranks then update their BatchNorm
+        # statistics locally.  An eval-mode forward (no statistics update) must therefore leave every rank with rank 0's.
+        a.model_access.eval()
+        a.model(batch(99, rank)[0])
+        a.model_access.train()
+        bufs = torch.cat([b.detach().float().reshape(-1) for b in a.model_access.buffers()])
+        # every rank reports the same (mean) loss
+        lt = torch.tensor(la, device="cuda", dtype=torch.float64)
+        b = make()
+        b.load(path, tag)
+        lb = run(b, range(6, 12))
+        wb = b.optimizer.path.gather_master()
+        out[name] = {
+            "replicas_identical": all_equal(a.optimizer.path.p_flat.float()),
+            "buffers_identical": all_equal(bufs),
+            "loss_identical_across_ranks": all_equal(lt),
+            "resume_bit_identical": bool(torch.equal(wa, wb)) and la[6:] == lb,
+            "opt_steps": a._optimizer_steps, "sharded": a.optimizer.path.sharded,
+            "loss_first_last": [la[0], la[-1]],
+        }
+        del a, b
+    return out
 
 
 if __name__ == "__main__":

@@ -37,5 +37,9 @@ def test_multi_gpu_parity(world, tmp_path):
         if r["norm_rel_err"] is not None:
             assert r["norm_rel_err"] < 1e-5, (name, r)
     assert res["loss_sync"] == res["loss_sync_expected"]
+    for name, r in res["stoke_api"].items():
+        assert r["replicas_identical"] and r["buffers_identical"] and r["loss_identical_across_ranks"], (name, r)
+        assert r["resume_bit_identical"], (name, r)
+        assert r["opt_steps"] == 6 and r["sharded"] == (name != "ddp"), (name, r)
     inf = res["inf_skip"]
     assert inf["unchanged"] and inf["scale"] == 128.0 and inf["skipped"] == 1 and inf["steps"] == 0
