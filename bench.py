@@ -219,6 +219,10 @@ def main():
     for key, kind in (("k1", 0), ("k2", 1)):
         tot, cnt = eng.profile_read(kind)
         k_ms[key] = tot / max(cnt, 1)
+    k1_dev_ms, k1_dev_n = eng.profile_read_k1_device()
+    # the device timer brackets the data phase between K1's barriers; at W = 1 there are no barriers (block 0 would only
+    # time its own chunk), so the event pair recorded around the launch is the kernel time there
+    k_ms["k1_device"] = k1_dev_ms / max(k1_dev_n, 1) if world > 1 else k_ms["k1"]
     eng.profile(False)
 
     # ---- timed region 2: end to end (H2D of the batch + D2H of the loss inside the timed region) ----
@@ -238,7 +242,12 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     n_local, n = path.n_local, path.n
     k2_bytes = n_local * 30  # g,p,m,v read (16) + p,m,v write (12) + bf16 param write (2), per element
-    k1_bytes = (n // world) * (2 * world + 4 * (world if not path.sharded else 1)) if world > 1 else n * (2 + 4 + 2)
+    # K1 at W = 1: HBM bytes (read bf16 grad, write fp32 main grad, zero the bucket).  At W > 1: bytes crossing each
+    # direction of this GPU's NVLink = (W-1)/W * n * (b_in + b_out), b_in = 2 (bf16), b_out = 4 (fp32; 0 when sharded)
+    if world > 1:
+        k1_bytes = (world - 1) / world * n * (2 + (0 if path.sharded else 4))
+    else:
+        k1_bytes = n * (2 + 4 + 2)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
@@ -249,11 +258,15 @@ def main():
                 "achieved": k2_bytes / (k_ms["k2"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": k2_bytes / (k_ms["k2"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                 "bytes_per_launch": k2_bytes, "ms_per_launch": k_ms["k2"], "peak_source": peak_src,
-                "k1": {"kernel": "k_grad_reduce (K1)", "bytes_per_launch": k1_bytes, "ms_per_launch": k_ms["k1"],
-                       "achieved": k1_bytes / (k_ms["k1"] * 1e-3) / 1e9,
+                "k1": {"kernel": "k_grad_reduce (K1)", "bytes_per_launch": k1_bytes,
+                       "ms_per_launch_events": k_ms["k1"], "ms_per_launch": k_ms["k1_device"],
+                       "achieved": k1_bytes / (k_ms["k1_device"] * 1e-3) / 1e9, "unit": "GB/s",
                        "bound": "hbm" if world == 1 else "nvlink",
-                       "note": "W=1: read bf16 grad + write fp32 main grad + zero the bucket (8 B/elem); "
-                               "W>1: peer reads + peer writes seen by this GPU's HBM"}}
+                       "peak": hbm_peak if world == 1 else 900.0,
+                       "frac": k1_bytes / (k_ms["k1_device"] * 1e-3) / 1e9 / (hbm_peak if world == 1 else 900.0),
+                       "note": "ms_per_launch: device timer between K1's start and end barriers (data phase; excludes the "
+                               "wait for the slowest rank's launch that ms_per_launch_events includes).  W=1: HBM bytes 8 B/elem; "
+                               "W>1: bytes per NVLink direction (W-1)/W*n*(2+4), peak = 900 GB/s nominal (770 measured peer copy)"}}
     samples = args.batch * world * args.steps
     line = {"metric": METRIC, "value": samples / (ms_total * 1e-3), "unit": METRIC, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

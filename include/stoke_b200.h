@@ -121,6 +121,9 @@ int stk_comm_check(stk_ctx* ctx, void* stream);
  * duration and the launch count since the last read, and clears the list. */
 int stk_profile_enable(stk_ctx* ctx, int on);
 int stk_profile_read(stk_ctx* ctx, int kind, double* ms_total, int* launches);
+/* K1 only: time between its start and end barriers taken with the device timer by block 0 (excludes the wait for the
+ * slowest rank to arrive, which host-side events include); synchronises `stream`. */
+int stk_profile_read_k1_device(stk_ctx* ctx, double* ms_total, int* launches, void* stream);
 
 /* ---- scaler / step state ------------------------------------------------------------------------------------------- */
 int stk_scaler_set(stk_ctx* ctx, const stk_scaler_state_t* st, void* stream);

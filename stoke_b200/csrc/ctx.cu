@@ -62,6 +62,8 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   cudaError_t e;
   if ((e = cudaMalloc(&c->scaler_dev, sizeof(stk_scaler_state_t))) != cudaSuccess ||
       (e = cudaMalloc(&c->accum_dev, sizeof(StepAccum))) != cudaSuccess ||
+      (e = cudaMalloc(&c->prof_ns_dev, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(c->prof_ns_dev, 0, 2 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaHostAlloc(&c->host_scratch, sizeof(double) * 16, cudaHostAllocMapped)) != cudaSuccess ||
       (e = cudaHostGetDevicePointer(&c->host_scratch_dev, c->host_scratch, 0)) != cudaSuccess) {
     delete c;
@@ -102,6 +104,7 @@ int stk_ctx_destroy(stk_ctx* c) {
   cudaFree(c->blk_partial_dev);
   cudaFree(c->grp_partial_dev);
   cudaFree(c->grp_count_dev);
+  cudaFree(c->prof_ns_dev);
   cudaFreeHost(c->host_scratch);
   delete c;
   return STK_OK;
@@ -295,6 +298,20 @@ int stk_profile_read(stk_ctx* c, int kind, double* ms_total, int* launches) {
   c->prof[kind].clear();
   *ms_total = tot;
   *launches = n;
+  return STK_OK;
+}
+
+int stk_profile_read_k1_device(stk_ctx* c, double* ms_total, int* launches, void* stream) {
+  STK_REQUIRE(c, c && ms_total && launches, "stk_profile_read_k1_device: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long v[2] = {0, 0};
+  STK_CUDA(c, cudaMemcpyAsync(v, c->prof_ns_dev, sizeof(v), cudaMemcpyDeviceToHost, s));
+  STK_CUDA(c, cudaMemsetAsync(c->prof_ns_dev, 0, sizeof(v), s));
+  STK_CUDA(c, cudaStreamSynchronize(s));
+  *ms_total = (double)v[0] * 1e-6;
+  *launches = (int)v[1];
   return STK_OK;
 }
 

@@ -42,6 +42,7 @@ struct stk_ctx {
   // optional launch timing (stk_profile_*): CUDA-event pairs recorded around the kernel launch, on the launch stream
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];  // 0: K1 reduce, 1: K2 optimizer step, 2: accumulate
+  unsigned long long* prof_ns_dev = nullptr;                   // {ns, launches} written by K1's block 0 (device timer)
   std::map<const void*, int> occupancy;                       // kernel -> resident blocks per SM (cached query)
   // pinned, mapped host scratch
   double* host_scratch = nullptr;     // [16]

@@ -28,6 +28,7 @@ struct ReduceParams {
   float* blk_partial;   // [grid] per-block norm partials
   float* grp_partial;   // [grid / 64 + 1] per-group partials
   uint32_t* grp_count;  // [grid / 64 + 1] group tickets
+  unsigned long long* prof_ns;  // optional {sum of barrier-to-barrier ns, launches} (block 0), nullptr when off
   size_t vec_begin, vec_end;  // owned shard in units of 8 elements
   float mul;
   float norm_p;
@@ -126,6 +127,10 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
   const bool zero_in = (p.flags & STK_RF_ZERO_INPUT) && W == 1;
 
   if (W > 1) block_barrier_all_ranks(p.pads, p.rank, W, 0, p.epoch);
+  // device-side timing of the data phase (after the start barrier = after the slowest rank has arrived, up to the end
+  // barrier): the NVLink time of this launch without the cross-rank launch skew that host-side events include
+  unsigned long long t_begin = 0;
+  if (p.prof_ns && blockIdx.x == 0 && threadIdx.x == 0) t_begin = globaltimer_ns();
 
   float inv_scale = 1.f;
   if (p.flags & STK_RF_UNSCALE) inv_scale = (float)(1.0 / (double)p.scaler->scale);
@@ -214,6 +219,10 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
   __syncthreads();
 
   if (W > 1) block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch);
+  if (p.prof_ns && blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&p.prof_ns[0], globaltimer_ns() - t_begin);
+    atomicAdd(&p.prof_ns[1], 1ull);
+  }
 
   // Only warp 0 stays for the bookkeeping: the other warps retire now, so a block never sits idle on the ticket's
   // fence + atomic round trip (that idle time cost ~40% at W == 1, where thousands of one-shot blocks pass through here).
@@ -388,6 +397,7 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   p.blk_partial = c->blk_partial_dev;
   p.grp_partial = c->grp_partial_dev;
   p.grp_count = c->grp_count_dev;
+  p.prof_ns = c->profiling ? c->prof_ns_dev : nullptr;
   size_t b = 0, e = 0;
   stk_shard_range(n, W, c->rank, &b, &e);
   p.vec_begin = b / 8;

@@ -184,6 +184,12 @@ class Engine:
         self._check(self.lib.stk_profile_read(self.ctx, kind, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_read_k1_device(self):
+        """(total ms, launches) of K1's barrier-to-barrier phase measured with the device timer."""
+        ms, n = C.c_double(), C.c_int()
+        self._check(self.lib.stk_profile_read_k1_device(self.ctx, C.byref(ms), C.byref(n), self._stream()))
+        return ms.value, n.value
+
     def comm_check(self):
         self._check(self.lib.stk_comm_check(self.ctx, self._stream()))
 
