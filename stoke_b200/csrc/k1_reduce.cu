@@ -30,6 +30,7 @@ struct ReduceParams {
   uint32_t* grp_count;  // [grid / 64 + 1] group tickets
   unsigned long long* prof_ns;  // optional {sum of barrier-to-barrier ns, launches} (block 0), nullptr when off
   size_t vec_begin, vec_end;  // owned shard in units of 8 elements
+  size_t vec_total, vec_per_shard;  // whole bucket / shard stride (for zeroing the local bucket after the end barrier)
   float mul;
   float norm_p;
   int rank, world, n_dst;
@@ -219,6 +220,18 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
   __syncthreads();
 
   if (W > 1) block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch);
+  if (W > 1 && (p.flags & STK_RF_ZERO_INPUT)) {
+    // Zero the LOCAL gradient bucket inside the kernel (no separate memset between backward and step).  Block b may only
+    // clear what the peers' blocks b have finished reading -- exactly this block's own index pattern, replicated in every
+    // shard: shard q of my bucket is read by rank q's block b at the same offsets, and that block has passed the end barrier.
+    for (int q = 0; q < W; ++q) {
+      const size_t qb = p.vec_per_shard * q;
+      size_t qe = qb + p.vec_per_shard;
+      if (qe > p.vec_total) qe = p.vec_total;
+      for (size_t v = qb + size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < qe; v += size_t(gridDim.x) * blockDim.x)
+        InVec<IN_DT>::zero(p.grad.p[p.rank], v);
+    }
+  }
   if (p.prof_ns && blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&p.prof_ns[0], globaltimer_ns() - t_begin);
     atomicAdd(&p.prof_ns[1], 1ull);
@@ -402,6 +415,8 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   stk_shard_range(n, W, c->rank, &b, &e);
   p.vec_begin = b / 8;
   p.vec_end = (e + 7) / 8;
+  p.vec_total = (n + 7) / 8;
+  p.vec_per_shard = ((n + 7) / 8 + W - 1) / W;
   p.mul = (float)mul;
   p.norm_p = (float)norm_p;
   p.rank = c->rank;
@@ -441,11 +456,6 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
 #undef STK_DISPATCH
   if (err != cudaSuccess) return stk_fail(c, STK_ERR_CUDA, std::string("k_grad_reduce launch: ") + cudaGetErrorString(err));
 
-  if ((flags & STK_RF_ZERO_INPUT) && W > 1) {
-    // peers were reading this bucket until the end barrier; the kernel boundary is the earliest safe point
-    const size_t esz = grad_dtype == STK_F32 ? 4 : 2;
-    STK_CUDA(c, cudaMemsetAsync(grad_ptrs[c->rank], 0, n * esz, s));
-  }
   return STK_OK;
 }
 

@@ -9,7 +9,6 @@ initial parameter broadcast).  Every byte of the per-step gradient path moves th
 ``csrc/``; if the library is missing or a call fails this module raises -- there is no torch fallback.
 """
 import ctypes as C
-import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -52,7 +51,6 @@ class Engine:
         self.device, self.rank, self.world, self.group = int(device), int(rank), int(world), group
         self._buffers: List[DeviceBuffer] = []
         self.launches = 0  # kernels launched through this engine (bench.py reports it as gpu_launches)
-        self._lock = threading.Lock()
         ctx = C.c_void_p()
         check(self.lib.stk_ctx_create(self.rank, self.world, self.device, 0, C.byref(ctx)))
         self.ctx = ctx
@@ -140,7 +138,7 @@ class Engine:
         self._check(self.lib.stk_grad_reduce(self.ctx, mode, _lib.ptr_array(grad_ptrs), _DT[grad_dtype], acc,
                                              _lib.ptr_array(out_ptrs), _DT[out_dtype], n, mul, norm_kind, norm_p, flags,
                                              self._stream()))
-        self.launches += 1 + (1 if (flags & _lib.RF_ZERO_INPUT and self.world > 1) else 0)
+        self.launches += 1
 
     def optim_step(self, hyper: _lib.OptimHyper, master_ptr: int, m_ptr: Optional[int], v_ptr: Optional[int],
                    grad_ptr: int, n_local: int, lp_ptrs: Optional[Sequence[int]], lp_dtype: torch.dtype,

@@ -76,7 +76,9 @@ class B200FusedOptimizer(torch.optim.Optimizer):
         self.path.clip = ClipSpec(_lib.CLIP_NORM, max_norm=max_norm, norm_type=norm_type)
 
     def consolidate_state_dict(self, recipient_rank: int = 0):
-        self._consolidated = self.state_dict()
+        """fairscale OSS gathers the shards on ``recipient_rank`` before ``state_dict()``; here ``state_dict()`` itself
+        all-gathers the sharded buffers on every rank, so this only exists for call-compatibility."""
+        return None
 
     # -- state dict in torch's per-parameter format ----------------------------------------------------------------------
     def _full(self, flat: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -89,18 +91,15 @@ class B200FusedOptimizer(torch.optim.Optimizer):
         st = path.engine.scaler_get()
         m, v, master = self._full(path.m_flat), self._full(path.v_flat), self._full(path.master_flat)
         state = {}
-        if st.opt_steps > 0 or True:
-            ms = path.unflatten(m) if m is not None else None
-            vs = path.unflatten(v) if v is not None else None
-            for i in range(len(path.params)):
-                entry = {}
-                if self._kind == _lib.OPT_SGD:
-                    entry["momentum_buffer"] = ms[i].clone() if ms is not None and st.opt_steps > 0 else None
-                else:
-                    entry["step"] = torch.tensor(float(st.opt_steps))
-                    entry["exp_avg"] = ms[i].clone()
-                    entry["exp_avg_sq"] = vs[i].clone()
-                state[i] = entry
+        ms = path.unflatten(m) if m is not None else None
+        vs = path.unflatten(v) if v is not None else None
+        for i in range(len(path.params)):
+            if self._kind == _lib.OPT_SGD:
+                # torch creates the buffer on the first step; before that (or without momentum) it is None
+                state[i] = {"momentum_buffer": ms[i].clone() if ms is not None and st.opt_steps > 0 else None}
+            else:
+                state[i] = {"step": torch.tensor(float(st.opt_steps)), "exp_avg": ms[i].clone(),
+                            "exp_avg_sq": vs[i].clone()}
         groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
         groups[0]["params"] = list(range(len(path.params)))
         return {"state": state, "param_groups": groups, "b200_master": master.clone(), "b200_opt_steps": int(st.opt_steps)}

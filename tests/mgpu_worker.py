@@ -88,6 +88,28 @@ def main(out_path):
                          "model_is_rounded_master": bool(torch.equal(path.p_flat.cpu(), got.to(path.model_dtype)))}
         del opt, path, net
 
+    # ---- full-size known-answer test (ResNet-50-sized bucket): exactly representable inputs -> exact expected output ----
+    class Big(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(25_557_032))
+
+    net = Big().cuda()
+    opt = B200FusedOptimizer(net, torch.optim.SGD, {"lr": 0.0}, engine=eng,
+                             clip=ClipSpec(_lib.CLIP_NORM, max_norm=1.0, norm_type=2.0), lp_dtype=torch.bfloat16)
+    path = opt.path
+    base = ((torch.arange(path.n, device="cuda") % 7) - 3).float()           # -3..3
+    path.g_flat.copy_((base * (rank + 1)).to(torch.bfloat16))                 # rank r contributes (r+1) * base
+    path.after_backward(sync=True, unscale=False)
+    expect = base * (world + 1) / 2.0                                         # mean over ranks of (r+1)
+    kat_ok = bool(torch.equal(path.main_flat, expect))
+    exp_norm = float(expect.double().pow(2).sum().sqrt())
+    got_norm = eng.scaler_get().grad_norm
+    zeroed = float(path.g_flat.float().abs().max()) == 0.0
+    results["kat_full_size"] = {"exact": kat_ok, "norm_rel_err": abs(got_norm - exp_norm) / exp_norm, "bucket_zeroed": zeroed}
+    eng.step_epilogue()
+    del opt, path, net
+
     # loss mean / barrier / inf propagation across ranks
     t = torch.tensor(float(rank + 1), device="cuda")
     results["loss_sync"] = eng.loss_sync(t)

@@ -37,6 +37,8 @@ def test_multi_gpu_parity(world, tmp_path):
         if r["norm_rel_err"] is not None:
             assert r["norm_rel_err"] < 1e-5, (name, r)
     assert res["loss_sync"] == res["loss_sync_expected"]
+    kat = res["kat_full_size"]
+    assert kat["exact"] and kat["bucket_zeroed"] and kat["norm_rel_err"] < 1e-6, kat
     for name, r in res["stoke_api"].items():
         assert r["replicas_identical"] and r["buffers_identical"] and r["loss_identical_across_ranks"], (name, r)
         assert r["resume_bit_identical"], (name, r)
