@@ -10,7 +10,8 @@
 namespace stk {
 
 constexpr int kMaxWorld = STK_MAX_WORLD;
-constexpr int kMaxBlocks = 1024;             // upper bound on the grid of any cross-rank kernel (flag slots per peer)
+constexpr int kMaxBlocks = 1024;
+constexpr int kMaxReduceBlocks = 256;        // grid bound of the cross-rank K1 (one block per SM)             // upper bound on the grid of any cross-rank kernel (flag slots per peer)
 constexpr uint64_t kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s: a dead peer becomes an error, not a hang
 
 // ---- signal pad layout (one per rank, peer-mapped) ------------------------------------------------------------------
@@ -23,8 +24,8 @@ struct RankScalars {       // what a rank publishes about its shard at the end o
 };
 struct SignalPad {
   uint32_t blk_flag[2][kMaxBlocks][kMaxWorld];  // [0]: start barrier, [1]: end barrier of block b, written by peer p
-  uint32_t aux_flag[4][kMaxWorld];              // 0: scalar exchange, 1: loss sync, 2: barrier kernel, 3: bcast
-  RankScalars scal[kMaxWorld];                  // slot p written by peer p
+  uint32_t aux_flag[4][kMaxWorld];              // 0: (unused), 1: loss sync, 2: barrier kernel, 3: (unused)
+  RankScalars blk_scal[kMaxWorld][kMaxReduceBlocks];  // [r][b]: norm partial / inf flag of rank r's K1 block b
   float loss_slot[2][kMaxWorld];                // double-buffered by call parity
   uint32_t error;                               // non-zero: a spin bound was hit on this rank
 };

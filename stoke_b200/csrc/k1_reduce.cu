@@ -219,7 +219,28 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
   }
   __syncthreads();
 
-  if (W > 1) block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch);
+  // block partial (warp 0): needed before the end barrier at W > 1, where it rides to the peers with the barrier flag
+  float blk = 0.f;
+  unsigned any_bad = 0;
+  if (threadIdx.x < 32) {
+    const unsigned nwarp = (blockDim.x + 31) >> 5;
+    blk = threadIdx.x < nwarp ? s_red[threadIdx.x] : 0.f;
+    blk = (p.norm_kind == STK_NORM_INF) ? warp_reduce<true>(blk) : warp_reduce<false>(blk);
+    any_bad = __any_sync(0xffffffffu, threadIdx.x < nwarp && s_bad[threadIdx.x] != 0);
+  }
+
+  if (W > 1) {
+    // Publish this block's (norm partial, inf flag) to every rank BEFORE signalling the end barrier: the same thread then
+    // does fence.sys + st.release of the flag, so whoever sees the flag sees the partial.  Every rank later sums all
+    // W x grid partials in the same (rank, block) order -> bit-identical totals everywhere, with no third cross-GPU
+    // round trip after the data phase.
+    if (threadIdx.x < (unsigned)W) {
+      RankScalars* slot = &p.pads.p[threadIdx.x]->blk_scal[p.rank][blockIdx.x];
+      st_relaxed_sys_f32(&slot->norm_partial, blk);
+      st_relaxed_sys_u32(&slot->found_inf, any_bad);
+    }
+    block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch);
+  }
   if (W > 1 && (p.flags & STK_RF_ZERO_INPUT)) {
     // Zero the LOCAL gradient bucket inside the kernel (no separate memset between backward and step).  Block b may only
     // clear what the peers' blocks b have finished reading -- exactly this block's own index pattern, replicated in every
@@ -238,17 +259,61 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
   }
 
   // Only warp 0 stays for the bookkeeping: the other warps retire now, so a block never sits idle on the ticket's
-  // fence + atomic round trip (that idle time cost ~40% at W == 1, where thousands of one-shot blocks pass through here).
+  // fence + atomic round trip.
   if (threadIdx.x >= 32) return;
   const unsigned lane = threadIdx.x;
-  const unsigned nwarp = (blockDim.x + 31) >> 5;
-  float blk = lane < nwarp ? s_red[lane] : 0.f;
-  blk = (p.norm_kind == STK_NORM_INF) ? warp_reduce<true>(blk) : warp_reduce<false>(blk);
-  const unsigned any_bad = __any_sync(0xffffffffu, lane < nwarp && s_bad[lane] != 0);
+  const bool mx = p.norm_kind == STK_NORM_INF;
+
+  if (W > 1) {
+    // ---- cross-rank flavour: plain ticket over the (<= SM count) co-resident blocks ----
+    unsigned last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = (atomicAdd(&p.accum->blocks_done, 1u) == gridDim.x - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    // every local block has passed its end barrier, so every peer block's partial has landed in this rank's pad
+    float total = 0.f;
+    unsigned inf = 0;
+    for (int r = 0; r < W; ++r) {
+      float x = 0.f;
+      for (unsigned b = lane; b < gridDim.x; b += 32) {
+        const RankScalars* slot = &p.pads.p[p.rank]->blk_scal[r][b];
+        const float y = ld_relaxed_sys_f32(&slot->norm_partial);
+        x = mx ? fmaxf(x, y) : x + y;
+        inf |= ld_relaxed_sys_u32(&slot->found_inf);
+      }
+      x = mx ? warp_reduce<true>(x) : warp_reduce<false>(x);
+      total = mx ? fmaxf(total, x) : total + x;
+    }
+    inf = __any_sync(0xffffffffu, inf != 0);
+    if (lane == 0) {
+      float run = p.accum->norm_partial;   // running over the buckets of this optimizer step (global values)
+      run = mx ? fmaxf(run, total) : run + total;
+      unsigned run_inf = p.accum->found_inf | (inf ? 1u : 0u);
+      p.accum->blocks_done = 0;
+      if (p.flags & STK_RF_FINAL) {
+        float norm = run;
+        if (p.norm_kind == STK_NORM_L2) norm = sqrtf(run);
+        else if (p.norm_kind == STK_NORM_P) norm = powf(run, 1.f / p.norm_p);
+        p.scaler->grad_norm = norm;
+        // the inf gate belongs to the loss scaler (GradScaler.step); without one the reference steps regardless
+        p.scaler->found_inf = (run_inf && (p.flags & STK_RF_UNSCALE)) ? 1 : 0;
+        run = 0.f;
+        run_inf = 0;
+      }
+      p.accum->norm_partial = run;
+      p.accum->found_inf = run_inf;
+    }
+    return;
+  }
+
+  // ---- local flavour (W == 1) ----
   // Two-level ticket (groups of 64 blocks): the last block of a group folds the group's partials, the last group folds
   // the group partials -- fixed order at both levels (deterministic), and the serial tail stays short even with the tens
   // of thousands of one-shot blocks of a W == 1 launch.
-  const bool mx = p.norm_kind == STK_NORM_INF;
   const unsigned grp = blockIdx.x >> 6, ngroups = (gridDim.x + 63) >> 6;
   const unsigned gsize = min(64u, gridDim.x - (grp << 6));
   unsigned last = 0;
@@ -298,33 +363,9 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
     __threadfence();
   }
   if (!(p.flags & STK_RF_FINAL)) return;
-  __syncwarp();
-  if (W > 1) {
-    if (lane < (unsigned)W) {
-      const int peer = lane;
-      RankScalars* slot = &p.pads.p[peer]->scal[p.rank];
-      st_relaxed_sys_f32(&slot->norm_partial, __ldcg(&p.accum->norm_partial));
-      st_relaxed_sys_u32(&slot->found_inf, atomicOr(&p.accum->found_inf, 0u));
-      __threadfence_system();
-      st_release_sys(&p.pads.p[peer]->aux_flag[0][p.rank], p.aux_epoch);
-      wait_flag(&p.pads.p[p.rank]->aux_flag[0][peer], p.aux_epoch, &p.pads.p[p.rank]->error);
-    }
-    __syncwarp();
-  }
   if (lane == 0) {
-    float total = 0.f;
-    uint32_t inf = 0;
-    if (W > 1) {
-      for (int r = 0; r < W; ++r) {  // rank order on every rank -> bit-identical totals everywhere
-        const RankScalars* slot = &p.pads.p[p.rank]->scal[r];
-        float y = ld_relaxed_sys_f32(&slot->norm_partial);
-        total = (p.norm_kind == STK_NORM_INF) ? fmaxf(total, y) : total + y;
-        inf |= ld_relaxed_sys_u32(&slot->found_inf);
-      }
-    } else {
-      total = p.accum->norm_partial;
-      inf = atomicOr(&p.accum->found_inf, 0u);
-    }
+    const float total = p.accum->norm_partial;
+    const uint32_t inf = atomicOr(&p.accum->found_inf, 0u);
     float norm = total;
     if (p.norm_kind == STK_NORM_L2) norm = sqrtf(total);
     else if (p.norm_kind == STK_NORM_P) norm = powf(total, 1.f / p.norm_p);
@@ -444,6 +485,7 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
     p.grp_count = c->grp_count_dev;
   }
   const bool coop = W > 1;
+  if (coop && grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
 
   cudaError_t err;
 #define STK_DISPATCH(IN, OUT) err = launch_reduce<IN, OUT>(c, p, grid, coop, s)
