@@ -254,9 +254,17 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch")
     except OSError:
         pass
-    roofline = {"kernel": "k_optim_step (K2 fused Adam + clip + bf16 param write)", "bound": "hbm",
-                "achieved": k2_bytes / (k_ms["k2"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": k2_bytes / (k_ms["k2"] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+    k2_bound, k2_peak, k2_name = "hbm", hbm_peak, "k_optim_step (K2 fused Adam + clip + bf16 param write)"
+    if path.sharded:
+        # sharded step: 1/W of the elements, and the updated bf16 shard is pushed to every rank from inside the kernel
+        # (parameter all-gather): NVLink-bound, (W-1)/W * n * 2 B per direction; timed by events, so rank skew is included
+        k2_bytes = (world - 1) / world * n * 2
+        k2_bound, k2_peak, peak_src = "nvlink", 900.0, "NVLink 5 nominal per direction"
+        k2_name = "k_optim_step (K2 sharded step + in-kernel bf16 parameter all-gather)"
+        traffic = None
+    roofline = {"kernel": k2_name, "bound": k2_bound,
+                "achieved": k2_bytes / (k_ms["k2"] * 1e-3) / 1e9, "peak": k2_peak, "unit": "GB/s",
+                "frac": k2_bytes / (k_ms["k2"] * 1e-3) / 1e9 / k2_peak, "traffic": traffic,
                 "bytes_per_launch": k2_bytes, "ms_per_launch": k_ms["k2"], "peak_source": peak_src,
                 "k1": {"kernel": "k_grad_reduce (K1)", "bytes_per_launch": k1_bytes,
                        "ms_per_launch_events": k_ms["k1"], "ms_per_launch": k_ms["k1_device"],
