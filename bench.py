@@ -219,7 +219,7 @@ def main():
     for key, kind in (("k1", 0), ("k2", 1)):
         tot, cnt = eng.profile_read(kind)
         k_ms[key] = tot / max(cnt, 1)
-    k1_dev_ms, k1_dev_n = eng.profile_read_k1_device()
+    k1_dev_ms, k1_dev_n, k1_zero_ms = eng.profile_read_k1_device()
     # the device timer brackets the data phase between K1's barriers; at W = 1 there are no barriers (block 0 would only
     # time its own chunk), so the event pair recorded around the launch is the kernel time there
     k_ms["k1_device"] = k1_dev_ms / max(k1_dev_n, 1) if world > 1 else k_ms["k1"]
@@ -268,13 +268,15 @@ def main():
                 "bytes_per_launch": k2_bytes, "ms_per_launch": k_ms["k2"], "peak_source": peak_src,
                 "k1": {"kernel": "k_grad_reduce (K1)", "bytes_per_launch": k1_bytes,
                        "ms_per_launch_events": k_ms["k1"], "ms_per_launch": k_ms["k1_device"],
+                       "ms_zero_tail": (k1_zero_ms / max(k1_dev_n, 1)) if world > 1 else 0.0,
                        "achieved": k1_bytes / (k_ms["k1_device"] * 1e-3) / 1e9, "unit": "GB/s",
                        "bound": "hbm" if world == 1 else "nvlink",
                        "peak": hbm_peak if world == 1 else 900.0,
                        "frac": k1_bytes / (k_ms["k1_device"] * 1e-3) / 1e9 / (hbm_peak if world == 1 else 900.0),
-                       "note": "ms_per_launch: device timer between K1's start and end barriers (data phase; excludes the "
-                               "wait for the slowest rank's launch that ms_per_launch_events includes).  W=1: HBM bytes 8 B/elem; "
-                               "W>1: bytes per NVLink direction (W-1)/W*n*(2+4), peak = 900 GB/s nominal (770 measured peer copy)"}}
+                       "note": "W>1: ms_per_launch = device timer between K1's start and end barriers = the NVLink phase (peer reads "
+                               "+ peer writes); excludes the wait for the slowest rank's launch (in ms_per_launch_events) and the "
+                               "local HBM zeroing of the bucket after the end barrier (ms_zero_tail); bytes per NVLink direction "
+                               "(W-1)/W*n*(2+4), peak 900 GB/s nominal (770 measured peer copy).  W=1: event-timed, HBM bytes 8 B/elem"}}
     samples = args.batch * world * args.steps
     line = {"metric": METRIC, "value": samples / (ms_total * 1e-3), "unit": METRIC, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -6,6 +6,7 @@
 
 Per size, device-timed (CUDA events on the launch stream, 10 warm-up + 50 timed back-to-back launches, max over ranks):
 
+  ours_*      default flavour of K1 (bulk-async staging); ours_ldg_*: the register-staged flavour, for comparison
   ours_bf16   K1 fused all-reduce, bf16 in -> bf16 out  (+ fused 1/W scale, inf test, sum-of-squares, cross-rank norm
               exchange): same wire bytes as NCCL, busbw = 2 (W-1)/W S / t
   ours_fp32   K1 as the training path uses it: bf16 in -> fp32 main grads out (b_out = 4): busbw = (W-1)/W n (2+4) / t
@@ -49,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-mb", type=int, default=1024)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--no-baselines", action="store_true", help="skip NCCL / symmetric-memory rows")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -96,6 +98,19 @@ def main():
         row["ours_fp32_us"] = t * 1e3
         row["ours_fp32_busbw"] = (world - 1) / world * n * 6 / (t * 1e-3) / 1e9
 
+        eng.set_k1_algo("ldg")
+        t = time_op(lambda: ours(O16, torch.bfloat16))
+        row["ours_ldg_bf16_us"] = t * 1e3
+        row["ours_ldg_bf16_busbw"] = 2 * (world - 1) / world * S / (t * 1e-3) / 1e9
+        t = time_op(lambda: ours(O32, torch.float32))
+        row["ours_ldg_fp32_us"] = t * 1e3
+        row["ours_ldg_fp32_busbw"] = (world - 1) / world * n * 6 / (t * 1e-3) / 1e9
+        eng.set_k1_algo("bulk")
+        if args.no_baselines:
+            rows.append(row)
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+            continue
         buf = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
         t = time_op(lambda: dist.all_reduce(buf))
         row["nccl_us"] = t * 1e3

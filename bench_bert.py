@@ -101,7 +101,7 @@ def main():
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         torch.distributed.all_reduce(tok)
     k2_ms, k2_n = eng.profile_read(1)
-    k1_ms, k1_n = eng.profile_read_k1_device()
+    k1_ms, k1_n, _ = eng.profile_read_k1_device()
     eng.profile(False)
     if rank == 0:
         sec = float(ms.item()) * 1e-3

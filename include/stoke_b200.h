@@ -116,14 +116,22 @@ int stk_comm_connect(stk_ctx* ctx, const unsigned char* handles);
 /* copies the device error word to the host (synchronises `stream`); returns STK_ERR_PEER if a spin bound was hit */
 int stk_comm_check(stk_ctx* ctx, void* stream);
 
+/* tuning knobs.  STK_OPT_K1_ALGO: how the cross-rank K1 brings the peers' 16-bit gradients into the SM -- 0 = 16-byte
+ * register loads, 1 = bulk-async copies (TMA engine) staged through shared memory (default; +10..20 % bus bandwidth).  Same
+ * results either way; fp32 gradients and launches with a local accumulator always take flavour 0.
+ * Also settable at context creation through the environment variable STK_K1_ALGO=ldg|bulk. */
+#define STK_OPT_K1_ALGO 1
+int stk_option_set(stk_ctx* ctx, int key, int value);
+
 /* launch timing for bench.py's roofline: when enabled, K1 (kind 0), K2 (kind 1) and the accumulate kernel (kind 2) are
  * bracketed by CUDA events on the launch stream; stk_profile_read synchronises those events, returns the summed
  * duration and the launch count since the last read, and clears the list. */
 int stk_profile_enable(stk_ctx* ctx, int on);
 int stk_profile_read(stk_ctx* ctx, int kind, double* ms_total, int* launches);
-/* K1 only: time between its start and end barriers taken with the device timer by block 0 (excludes the wait for the
- * slowest rank to arrive, which host-side events include); synchronises `stream`. */
-int stk_profile_read_k1_device(stk_ctx* ctx, double* ms_total, int* launches, void* stream);
+/* K1 only: time between its start and end barriers (the NVLink data phase) taken with the device timer by block 0 --
+ * excludes the wait for the slowest rank to arrive, which host-side events include; ms_zero_tail (may be NULL) receives
+ * the time block 0 then spent zeroing its part of the local bucket (HBM work).  Synchronises `stream`. */
+int stk_profile_read_k1_device(stk_ctx* ctx, double* ms_total, int* launches, double* ms_zero_tail, void* stream);
 
 /* ---- scaler / step state ------------------------------------------------------------------------------------------- */
 int stk_scaler_set(stk_ctx* ctx, const stk_scaler_state_t* st, void* stream);

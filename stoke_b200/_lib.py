@@ -16,6 +16,8 @@ NORM_NONE, NORM_L2, NORM_INF, NORM_P = 0, 1, 2, 3
 CLIP_NONE, CLIP_NORM, CLIP_VALUE = 0, 1, 2
 OPT_ADAM, OPT_ADAMW, OPT_SGD = 0, 1, 2
 RF_FINAL, RF_ZERO_INPUT, RF_UNSCALE = 1, 2, 4
+OPT_K1_ALGO = 1
+K1_ALGO_LDG, K1_ALGO_BULK = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_PEER, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
 
@@ -69,9 +71,10 @@ _SIGNATURES = {
     "stk_comm_local": (C.c_int, [_P, C.c_char_p]),
     "stk_comm_connect": (C.c_int, [_P, C.c_char_p]),
     "stk_comm_check": (C.c_int, [_P, _P]),
+    "stk_option_set": (C.c_int, [_P, C.c_int, C.c_int]),
     "stk_profile_enable": (C.c_int, [_P, C.c_int]),
     "stk_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
-    "stk_profile_read_k1_device": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), _P]),
+    "stk_profile_read_k1_device": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), _P]),
     "stk_scaler_set": (C.c_int, [_P, C.POINTER(ScalerState), _P]),
     "stk_scaler_get": (C.c_int, [_P, C.POINTER(ScalerState), _P]),
     "stk_scaler_scale_ptr": (_P, [_P]),

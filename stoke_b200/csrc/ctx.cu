@@ -1,4 +1,5 @@
 // ctx.cu -- context, peer-visible memory (CUDA IPC), signal pads, scaler state.  Host code + two tiny kernels.
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -59,11 +60,12 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   c->world = world;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* algo = std::getenv("STK_K1_ALGO")) c->k1_algo = (std::strcmp(algo, "bulk") == 0) ? 1 : 0;
   cudaError_t e;
   if ((e = cudaMalloc(&c->scaler_dev, sizeof(stk_scaler_state_t))) != cudaSuccess ||
       (e = cudaMalloc(&c->accum_dev, sizeof(StepAccum))) != cudaSuccess ||
-      (e = cudaMalloc(&c->prof_ns_dev, 2 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(c->prof_ns_dev, 0, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&c->prof_ns_dev, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(c->prof_ns_dev, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaHostAlloc(&c->host_scratch, sizeof(double) * 16, cudaHostAllocMapped)) != cudaSuccess ||
       (e = cudaHostGetDevicePointer(&c->host_scratch_dev, c->host_scratch, 0)) != cudaSuccess) {
     delete c;
@@ -273,6 +275,19 @@ int stk_scaler_get(stk_ctx* c, stk_scaler_state_t* st, void* stream) {
 
 void* stk_scaler_scale_ptr(stk_ctx* c) { return c ? static_cast<void*>(&c->scaler_dev->scale) : nullptr; }
 
+int stk_option_set(stk_ctx* c, int key, int value) {
+  STK_REQUIRE(c, c != nullptr, "stk_option_set: NULL ctx");
+  std::lock_guard<std::mutex> lk(c->mu);
+  switch (key) {
+    case STK_OPT_K1_ALGO:
+      STK_REQUIRE(c, value == 0 || value == 1, "stk_option_set: K1 algo must be 0 (ldg) or 1 (bulk)");
+      c->k1_algo = value;
+      return STK_OK;
+    default:
+      return stk_fail(c, STK_ERR_INVALID, "stk_option_set: unknown key");
+  }
+}
+
 int stk_profile_enable(stk_ctx* c, int on) {
   STK_REQUIRE(c, c != nullptr, "stk_profile_enable: NULL ctx");
   std::lock_guard<std::mutex> lk(c->mu);
@@ -301,17 +316,18 @@ int stk_profile_read(stk_ctx* c, int kind, double* ms_total, int* launches) {
   return STK_OK;
 }
 
-int stk_profile_read_k1_device(stk_ctx* c, double* ms_total, int* launches, void* stream) {
+int stk_profile_read_k1_device(stk_ctx* c, double* ms_total, int* launches, double* ms_zero_tail, void* stream) {
   STK_REQUIRE(c, c && ms_total && launches, "stk_profile_read_k1_device: NULL argument");
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  unsigned long long v[2] = {0, 0};
+  unsigned long long v[4] = {0, 0, 0, 0};
   STK_CUDA(c, cudaMemcpyAsync(v, c->prof_ns_dev, sizeof(v), cudaMemcpyDeviceToHost, s));
   STK_CUDA(c, cudaMemsetAsync(c->prof_ns_dev, 0, sizeof(v), s));
   STK_CUDA(c, cudaStreamSynchronize(s));
   *ms_total = (double)v[0] * 1e-6;
   *launches = (int)v[1];
+  if (ms_zero_tail) *ms_zero_tail = (double)v[2] * 1e-6;
   return STK_OK;
 }
 

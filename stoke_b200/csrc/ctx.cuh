@@ -32,6 +32,7 @@ struct stk_ctx {
   bool comm_ready = false;
   uint32_t blk_epoch = 0;       // block-barrier epoch (identical sequence on every rank)
   uint32_t aux_epoch[4] = {0, 0, 0, 0};
+  int k1_algo = 1;              // cross-rank K1 flavour: 0 = register-staged loads (k1_reduce.cu), 1 = bulk-async (k1_bulk.cu, default)
   // device state
   stk_scaler_state_t* scaler_dev = nullptr;
   StepAccum* accum_dev = nullptr;

@@ -172,6 +172,10 @@ class Engine:
         self._check(self.lib.stk_bcast(self.ctx, _lib.ptr_array(buf.peer_ptrs(offset_bytes)), nbytes, root, self._stream()))
         self.launches += 1
 
+    def set_k1_algo(self, algo: str):
+        """Cross-rank K1 flavour: "ldg" (register-staged 16-byte loads) or "bulk" (bulk-async copies through shared memory)."""
+        self._check(self.lib.stk_option_set(self.ctx, _lib.OPT_K1_ALGO, {"ldg": 0, "bulk": 1}[algo]))
+
     def profile(self, on: bool):
         """Brackets K1 / K2 / accumulate launches with CUDA events inside the library (for bench.py's roofline)."""
         self._check(self.lib.stk_profile_enable(self.ctx, int(on)))
@@ -183,10 +187,10 @@ class Engine:
         return ms.value, n.value
 
     def profile_read_k1_device(self):
-        """(total ms, launches) of K1's barrier-to-barrier phase measured with the device timer."""
-        ms, n = C.c_double(), C.c_int()
-        self._check(self.lib.stk_profile_read_k1_device(self.ctx, C.byref(ms), C.byref(n), self._stream()))
-        return ms.value, n.value
+        """(ms of K1's barrier-to-barrier NVLink phase, launches, ms of the bucket-zeroing tail) from the device timer."""
+        ms, n, z = C.c_double(), C.c_int(), C.c_double()
+        self._check(self.lib.stk_profile_read_k1_device(self.ctx, C.byref(ms), C.byref(n), C.byref(z), self._stream()))
+        return ms.value, n.value, z.value
 
     def comm_check(self):
         self._check(self.lib.stk_comm_check(self.ctx, self._stream()))

@@ -13,21 +13,23 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, tmp_path, port):
-    out = tmp_path / f"mgpu_{world}.json"
+def _run(world, tmp_path, port, algo="ldg"):
+    out = tmp_path / f"mgpu_{world}_{algo}.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), str(out)]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    env = dict(os.environ, STK_K1_ALGO=algo)  # cross-rank K1 flavour: register-staged loads | bulk-async through smem
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-4000:]
     with open(out) as f:
         return json.load(f)
 
 
+@pytest.mark.parametrize("algo", ["ldg", "bulk"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_gpu_parity(world, tmp_path):
+def test_multi_gpu_parity(world, algo, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    res = _run(world, tmp_path, 29500 + world)
+    res = _run(world, tmp_path, 29500 + world + (10 if algo == "bulk" else 0), algo)
     for name, r in res.items():
         if not isinstance(r, dict) or "rel_err" not in r:
             continue
