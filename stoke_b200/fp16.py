@@ -80,6 +80,10 @@ class BaseFP16:
             self._print_device(f"FP16 Mixin: Initialized scaler of type {type(self._scaler).__name__}")
 
     def wrap_fp16(self, model, optimizer=None):
+        if self._scaler is None and getattr(self, "_engine", None) is not None:
+            # no loss scaling in this mode: make sure a scaler left enabled by an earlier Stoke object in this process
+            # (the state lives in the per-process engine) does not unscale / gate this one
+            self._engine.scaler_set(enabled=0, scale=1.0, growth_tracker=0, found_inf=0)
         self._scaler_info()
         return model, optimizer
 
