@@ -34,7 +34,13 @@ class FakeRunner:
     def detach_and_sync_loss(self, loss, device=None): return loss.item()
     def grad_accum_context(self, model): self.calls.append("no_sync"); return nullcontext()
     def step_context(self, optimizer): return nullcontext()
-    def backward_call(self, loss, model, optimizer): self.calls.append("backward"); loss.backward()
+    def backward_call(self, loss, model, optimizer):
+        self.calls.append("backward")
+        if isinstance(loss, (list, tuple)):
+            for idx, val in enumerate(loss):
+                val.backward(retain_graph=(idx == 0))
+        else:
+            loss.backward()
     def clip_grad(self, grad_clip, model, optimizer, **kw):
         self.calls.append("clip")
         torch.nn.utils.clip_grad_norm_(model.parameters(), grad_clip.max_norm, grad_clip.norm_type)
@@ -45,7 +51,7 @@ class FakeRunner:
 
 @pytest.fixture
 def fake_stoke(monkeypatch):
-    def make(model, accum, clip=None, optimizer=torch.optim.Adam, kwargs=None):
+    def make(model, accum, clip=None, optimizer=torch.optim.Adam, kwargs=None, loss=None):
         kwargs = synthetic.CFG1_ADAM if kwargs is None else kwargs
         holder = {}
 
@@ -57,7 +63,8 @@ def fake_stoke(monkeypatch):
         monkeypatch.setattr(status_mod, "_cuda_available", lambda: True)
         monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, device=None: self)
         s = sb.Stoke(model=model, optimizer=sb.StokeOptimizer(optimizer=optimizer, optimizer_kwargs=kwargs),
-                     loss=torch.nn.BCEWithLogitsLoss(), batch_size_per_device=32, grad_accum_steps=accum,
+                     loss=loss if loss is not None else torch.nn.BCEWithLogitsLoss(), batch_size_per_device=32,
+                     grad_accum_steps=accum,
                      grad_clip=clip, gpu=True, verbose=False)
         return s, holder["r"]
     return make
@@ -139,3 +146,31 @@ def test_exports_cover_reference_names():
     assert expected <= set(sb.__all__)
     for name in expected:
         assert hasattr(sb, name)
+
+
+def test_multiple_losses_bookkeeping_matches_live_reference(fake_stoke, reference_stoke):
+    """List / tuple of loss callables (stoke/stoke.py:889-901): per-loss synced values, aggregated sums, EMA, the division by
+    grad_accum, and the retain_graph backward over the list -- side by side with the unmodified reference on CPU."""
+    ref = reference_stoke
+
+    def losses():
+        return [torch.nn.BCEWithLogitsLoss(), lambda out, y: ((out - y) ** 2).mean()]
+
+    m_ref, m_new = synthetic.basic_nn(8), synthetic.basic_nn(8)
+    with redirect_stdout(io.StringIO()):
+        s_ref = ref.Stoke(model=m_ref, optimizer=ref.StokeOptimizer(optimizer=torch.optim.Adam,
+                          optimizer_kwargs=synthetic.CFG1_ADAM), loss=losses(), batch_size_per_device=32,
+                          grad_accum_steps=2, gpu=False, verbose=False)
+    s_new, _ = fake_stoke(m_new, 2, loss=losses())
+    for x, y in synthetic.cfg1_batches(9, seed=4):
+        for s in (s_ref, s_new):
+            l = s.loss(s.model(x), y)
+            assert isinstance(l, list) and len(l) == 2
+            s.backward(l)
+            s.step()
+        assert s_ref.step_loss == s_new.step_loss
+        assert s_ref._agg_loss == s_new._agg_loss
+        assert s_ref.ema_loss == s_new.ema_loss
+    a = torch.cat([p.detach().reshape(-1) for p in m_ref.parameters()])
+    b = torch.cat([p.detach().reshape(-1) for p in m_new.parameters()])
+    assert torch.equal(a, b)
