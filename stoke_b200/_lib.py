@@ -107,9 +107,15 @@ def load():
     with _lock:
         if _lib is None:
             if not os.path.exists(LIB_PATH):
-                raise StokeB200Error(
-                    ERR_STATE, f"{LIB_PATH} is missing -- build it with `python stoke_b200/csrc/build.py` "
-                    f"(there is no non-CUDA fallback)")
+                # not a fallback: the only way forward is the CUDA library, so try to compile it in-tree (nvcc, sm_100a)
+                try:
+                    from .csrc.build import build as _build
+
+                    _build()
+                except Exception as e:  # noqa: BLE001
+                    raise StokeB200Error(
+                        ERR_STATE, f"{LIB_PATH} is missing and could not be built ({type(e).__name__}: {e}) -- build it "
+                        f"with `python stoke_b200/csrc/build.py` (there is no non-CUDA fallback)") from e
             lib = C.CDLL(LIB_PATH)
             for name, (res, args) in _SIGNATURES.items():
                 fn = getattr(lib, name)
