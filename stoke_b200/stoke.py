@@ -216,10 +216,11 @@ class Stoke:
                                            pre_backwards: bool = True, single_line: bool = False):
         check_fn = self._check_pre_accum if pre_backwards else self._check_accum
         if check_fn():
-            div = self.grad_accum
-            val = type(self._agg_loss)(v / div for v in self._agg_loss) if isinstance(self._agg_loss, (list, tuple)) \
-                else self._agg_loss / div
-            self.print(self._fmt(prepend_msg, val), single_line=single_line)
+            if isinstance(self._agg_loss, (list, tuple)):
+                # the reference prints the bare scaled values for multiple losses (stoke.py:431-433)
+                self.print([val / self.grad_accum for val in self._agg_loss], single_line=single_line)
+            else:
+                self.print(f"{prepend_msg}: {self._agg_loss / self.grad_accum:.3f}")
 
     def print_synced_loss(self, loss, prepend_msg: str = "Step Synced Loss", device=None, single_line: bool = False):
         self.print(self._fmt(prepend_msg, self.detach_and_sync_loss(loss, device), multiplier=self.grad_accum),
