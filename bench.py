@@ -35,7 +35,7 @@ CPU_SAMPLE_BATCH = 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
