@@ -46,15 +46,17 @@ def time_op(fn, warmup=10, iters=50):
     return float(ms.item())
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-mb", type=int, default=1024)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-baselines", action="store_true", help="skip NCCL / symmetric-memory rows")
-    args = ap.parse_args()
+    ap.add_argument("--json-line", action="store_true", help="print ONE bench.py-shaped JSON line (bench.py --workload allreduce_sweep)")
+    args = ap.parse_args(argv)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from stoke_b200 import _lib
     from stoke_b200.engine import get_engine
@@ -63,9 +65,10 @@ def main():
     sizes = [s for s in (64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20, 1 << 30)
              if s <= args.max_mb << 20]
     n_max = max(sizes) // 2
-    G = eng.alloc(n_max * 2)
-    O16 = eng.alloc(n_max * 2)
-    O32 = eng.alloc(n_max * 4)
+    G = eng.alloc(n_max * 2, multicast=True)
+    O16 = eng.alloc(n_max * 2, multicast=True)
+    O32 = eng.alloc(n_max * 4, multicast=True)
+    have_nvls = bool(G.mc_ptr and O16.mc_ptr and O32.mc_ptr)
     g = G.tensor(torch.bfloat16, n_max)
     torch.manual_seed(2000 + rank)
     g.copy_(torch.randn(n_max, device="cuda") * 1e-3)
@@ -106,6 +109,16 @@ def main():
         row["ours_ldg_fp32_us"] = t * 1e3
         row["ours_ldg_fp32_busbw"] = (world - 1) / world * n * 6 / (t * 1e-3) / 1e9
         eng.set_k1_algo("bulk")
+        if have_nvls:
+            # multimem flavour: the NVSwitch reduces (multimem.ld_reduce) and replicates (multimem.st)
+            eng.set_k1_algo("nvls")
+            t = time_op(lambda: ours(O16, torch.bfloat16))
+            row["ours_nvls_bf16_us"] = t * 1e3
+            row["ours_nvls_bf16_busbw"] = 2 * (world - 1) / world * S / (t * 1e-3) / 1e9
+            t = time_op(lambda: ours(O32, torch.float32))
+            row["ours_nvls_fp32_us"] = t * 1e3
+            row["ours_nvls_fp32_busbw"] = (world - 1) / world * n * 6 / (t * 1e-3) / 1e9
+            eng.set_k1_algo("bulk")
         if args.no_baselines:
             rows.append(row)
             if rank == 0:
@@ -155,13 +168,34 @@ def main():
     dist.all_reduce(ref)
     ref /= world
     ok = bool(torch.allclose(mine, ref, rtol=1e-6, atol=1e-9))
+    nvls_ok = None
+    if have_nvls:
+        # the multimem flavour on the same data: equal to the exact flavours up to the bf16 rounding of the switch's sum
+        eng.set_k1_algo("nvls")
+        eng.grad_reduce(_lib.REDUCE_ALL, G.peer_ptrs(), torch.bfloat16, None, O32.peer_ptrs(), torch.float32, n, 1.0 / world,
+                        _lib.NORM_L2, 2.0, _lib.RF_FINAL)
+        eng.set_k1_algo("bulk")
+        mm = O32.tensor(torch.float32, n)[: 1 << 20].clone()
+        nvls_ok = bool(torch.allclose(mm, ref, rtol=2.0**-7, atol=1e-9))
     if rank == 0:
-        summary = {"world": world, "rows": rows, "spot_check_ok": ok,
+        summary = {"world": world, "rows": rows, "spot_check_ok": ok, "nvls_spot_check_ok": nvls_ok, "nvls": have_nvls,
                    "nvlink_nominal_gbs": 900, "nvlink_measured_peer_copy_gbs": 770}
         if args.out:
             with open(args.out, "w") as f:
                 json.dump(summary, f, indent=1)
-        print("spot check", ok)
+        if args.json_line:
+            big = rows[-1]
+            best = max((big.get(k, 0.0), k) for k in ("ours_bf16_busbw", "ours_ldg_bf16_busbw", "ours_nvls_bf16_busbw"))
+            print(json.dumps({"metric": "fused grad all-reduce bus bandwidth (NCCL convention 2(W-1)/W*S/t), largest bucket",
+                              "value": best[0], "unit": "GB/s", "n_gpus": world, "steps": 50, "warmup": 10,
+                              "ms_per_step": big[best[1].replace("_busbw", "_us")] * 1e-3, "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                              "config": {"workload": "grad_allreduce_sweep_64KB_1GB", "flavour": best[1], "l2": "buckets >= 256 MB exceed L2"},
+                              "roofline": {"bound": "nvlink", "achieved": best[0], "peak": 900.0, "unit": "GB/s",
+                                           "frac": best[0] / 900.0, "traffic": None}, "rows": rows,
+                              "spot_check_ok": ok, "nvls_spot_check_ok": nvls_ok}))
+        else:
+            print("spot check", ok, "nvls", nvls_ok)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,7 +1,12 @@
 # -*- coding: utf-8 -*-
-"""Kernel-level roofline of the engine on one B200: K1 at W=1 (cast + unscale + accumulate + norm + inf + bucket zeroing),
-the local accumulate kernel, and K2 (fused Adam/AdamW/SGD + clip + bf16 parameter write), on flat buffers of ResNet-50
-size (25.6 M elements) and BERT-base size (109.5 M elements).
+"""Kernel-level roofline of the engine on one B200, on flat buffers of ResNet-50 size (25.6 M elements) and BERT-base size
+(109.5 M elements):
+
+  local route (the world-1 training path)   k_grad_norm (2 B/elem: one read of the raw bf16 bucket) and k_optim_step reading
+                                            and zeroing the raw bucket (30 B/elem), timed separately and back to back
+  main route                                k_grad_reduce at W=1 (6 B/elem algorithmic: read grad, write fp32 main grad; + 2
+                                            for the bucket zeroing) and k_optim_step on fp32 main grads (30 B/elem)
+  k_grad_accumulate                         the local no-sync micro-step
 
     python bench_kernels.py [--out profiles/kernels_rNN.json]
 
@@ -70,30 +75,46 @@ def main():
         for optim_cls, kw, lp, tag in ((torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, "adam_bf16"),
                                        (torch.optim.Adam, {"lr": 1e-3}, None, "adam_fp32"),
                                        (torch.optim.SGD, {"lr": 0.1, "momentum": 0.9}, torch.bfloat16, "sgdm_bf16")):
-            net = Flat(n).cuda()
-            opt = B200FusedOptimizer(net, optim_cls, kw, engine=eng, grad_accum=2,
-                                     clip=ClipSpec(_lib.CLIP_NORM, max_norm=1.0, norm_type=2.0), lp_dtype=lp)
-            path = opt.path
-            path.g_flat.copy_((torch.randn(path.n, device="cuda") * 1e-3).to(path.g_flat.dtype))
             gsz = 2 if lp is not None else 4
             flush_l2 = n < 60_000_000
-            npad = path.n
-            # K1 at W=1: read grad, write fp32 main grad, zero the bucket
-            timed(lambda: path.after_backward(sync=True, unscale=False), npad * (gsz + 4 + gsz), f"k_grad_reduce[W=1,{tag}]",
-                  size_name, flush_l2)
-            path.g_flat.copy_((torch.randn(path.n, device="cuda") * 1e-3).to(path.g_flat.dtype))
-            timed(lambda: eng.grad_accumulate(path.G.ptr, path.model_dtype, path.ACC.ptr, npad, first=False, zero_grad=True),
-                  npad * (gsz + 4 + 4 + gsz), f"k_grad_accumulate[{tag}]", size_name, flush_l2)
-            path.main_flat.copy_(torch.randn(path.n, device="cuda") * 1e-3)
             per = {"adam_bf16": 30, "adam_fp32": 28, "sgdm_bf16": 22}[tag]
-            hyper = opt._hyper()
+            for route in ("local", "main"):
+                net = Flat(n).cuda()
+                opt = B200FusedOptimizer(net, optim_cls, kw, engine=eng, grad_accum=2, route=route,
+                                         clip=ClipSpec(_lib.CLIP_NORM, max_norm=1.0, norm_type=2.0), lp_dtype=lp)
+                path = opt.path
+                npad = path.n
+                hyper = opt._hypers()
 
-            def k2():
-                path.optimizer_step(hyper)
+                def fill():
+                    path.g_flat.copy_((torch.randn(path.n, device="cuda") * 1e-3).to(path.g_flat.dtype))
 
-            timed(k2, npad * per, f"k_optim_step[{tag}] (+epilogue)", size_name, flush_l2)
-            del opt, path, net
-            torch.cuda.empty_cache()
+                fill()
+                if route == "local":
+                    # the norm pass reads the bucket and writes nothing: it can be timed in isolation
+                    timed(lambda: path.after_backward(sync=True, unscale=False), npad * gsz, f"k_grad_norm[{tag}]",
+                          size_name, flush_l2)
+                    # the fused step consumes (zeroes) the bucket; its traffic does not depend on the values
+                    timed(lambda: path.optimizer_step(hyper), npad * (per + (gsz - 4) + gsz), f"k_optim_step[raw,{tag}] (+epilogue)",
+                          size_name, flush_l2)
+
+                    def both():
+                        path.after_backward(sync=True, unscale=False)
+                        path.optimizer_step(hyper)
+
+                    # back to back WITHOUT a flush in between: the step's read of the bucket can hit L2
+                    timed(both, npad * (gsz + per + (gsz - 4) + gsz), f"k_grad_norm+k_optim_step[raw,{tag}]", size_name, flush_l2)
+                else:
+                    timed(lambda: path.after_backward(sync=True, unscale=False), npad * (gsz + 4), f"k_grad_reduce[W=1,{tag}]",
+                          size_name, flush_l2)
+                    fill()
+                    timed(lambda: eng.grad_accumulate(path.G.ptr, path.model_dtype, path.ACC.ptr, npad, first=False, zero_grad=True),
+                          npad * (gsz + 4 + 4 + gsz), f"k_grad_accumulate[{tag}]", size_name, flush_l2)
+                    path.main_flat.copy_(torch.randn(path.n, device="cuda") * 1e-3)
+                    timed(lambda: path.optimizer_step(hyper), npad * per, f"k_optim_step[main,{tag}] (+epilogue)", size_name, flush_l2)
+                opt.close()
+                del opt, path, net
+                torch.cuda.empty_cache()
     if args.out:
         with open(args.out, "w") as f:
             json.dump({"peak_hbm_gbs": peak, "rows": rows}, f, indent=1)

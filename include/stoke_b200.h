@@ -23,6 +23,15 @@
  *   stk_bcast                        DDP init param sync / per-forward buffer broadcast (broadcast_buffers=True,
  *                                    stoke/configs.py:182)
  *   stk_randperm / stk_argsort_u32 / stk_sampler_*    BucketedDistributedSampler  stoke/data.py:156-266, 380-498
+ *   stk_state_*                      one scaler / step-counter / norm state per optimizer (the reference keeps them per
+ *                                    GradScaler / per optimizer object: stoke/fp16.py:733-806, stoke/extensions.py:53-78)
+ *   stk_multicast_try_bind           NCCL's NVLS transport under DDP (stoke/extensions.py:207-215): an NVSwitch multicast
+ *                                    mapping of a peer-visible buffer, used by the multimem flavour of stk_grad_reduce
+ *   stk_grad_norm                    the two reduction passes of clip_grad_norm_ + GradScaler.unscale_'s inf test
+ *                                    (stoke/fp16.py:180-183, 233) when there is no cross-rank reduce to fuse them into
+ *   stk_grad_scale                   clip_grad_norm_'s scaling pass / clip_grad_value_ (stoke/fp16.py:184, 233) for the
+ *                                    stock-optimizer route (any torch.optim class, stoke/extensions.py:53-78)
+ *   stk_loss_sync_begin/_wait        detach_and_sync_loss without the per-micro-step host synchronisation
  */
 #ifndef STOKE_B200_H
 #define STOKE_B200_H
@@ -68,7 +77,8 @@ typedef struct {
   int sm_major, sm_minor, sm_count;
   int rank, world, device;
   int peer_access;        /* 1 if every peer's memory is mapped */
-  int multicast;          /* 1 if NVLS multicast objects can be created on this device (not used yet) */
+  int multicast;          /* 1 if the device reports CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED and the driver's VMM / multicast
+                             entry points resolved (whether a given buffer is bound: stk_multicast_try_bind) */
   size_t hbm_bytes;
 } stk_caps_t;
 
@@ -104,24 +114,47 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
 int stk_ctx_destroy(stk_ctx* ctx);
 int stk_caps(stk_ctx* ctx, stk_caps_t* out);
 
-/* ---- peer-visible device memory (cudaMalloc + CUDA IPC; the 64-byte handles are exchanged by the caller) ---------- */
+/* ---- peer-visible device memory; the 64-byte handles are exchanged by the caller ------------------------------------
+ * Two back ends behind the same calls (STK_OPT_MEM_MODE / env STK_MEM=ipc|vmm, default vmm when world > 1 and the driver
+ * supports it): "vmm" = cuMemCreate + POSIX file-descriptor export (the descriptor travels over a unix socket served by the
+ * owning context) -- required for NVLS multicast; "ipc" = cudaMalloc + cudaIpc*.  All ranks must use the same mode. */
 int stk_mem_alloc_shared(stk_ctx* ctx, size_t bytes, void** local_ptr, unsigned char handle_out[STK_IPC_HANDLE_BYTES]);
-/* handles: world * 64 bytes in rank order; peer_ptrs_out[rank] == local_ptr */
+/* handles: world * 64 bytes in rank order; peer_ptrs_out[rank] == local_ptr.  In vmm mode this also imports the multicast
+ * object rank 0 created for the buffer (if any) and adds this rank's device to it. */
 int stk_mem_open_peers(stk_ctx* ctx, void* local_ptr, const unsigned char* handles, void** peer_ptrs_out);
 int stk_mem_free_shared(stk_ctx* ctx, void* local_ptr);
+/* Binds the buffer's memory to its multicast object and maps it: *mc_ptr_out is an address whose loads/stores address the
+ * same offset of EVERY rank's buffer (multimem.* instructions).  Collective: call on every rank after every rank has returned
+ * from stk_mem_open_peers (caller barrier), and barrier again before the first use.  Returns STK_ERR_UNSUPPORTED (and leaves
+ * the buffer fully usable through its peer pointers) when the device, driver or buffer has no multicast support.
+ * stk_multicast_release undoes a bind (used when some other rank failed to bind). */
+int stk_multicast_try_bind(stk_ctx* ctx, void* local_ptr, void** mc_ptr_out);
+int stk_multicast_release(stk_ctx* ctx, void* local_ptr);
 
 /* signal pads (flags + scalar slots) used by every cross-rank kernel: two-phase like the buffers above */
 int stk_comm_local(stk_ctx* ctx, unsigned char handle_out[STK_IPC_HANDLE_BYTES]);
 int stk_comm_connect(stk_ctx* ctx, const unsigned char* handles);
 /* copies the device error word to the host (synchronises `stream`); returns STK_ERR_PEER if a spin bound was hit */
 int stk_comm_check(stk_ctx* ctx, void* stream);
+/* same verdict without synchronising: reads the error word's mirror in mapped host memory (a kernel that gave up on a peer
+ * writes it).  Every cross-rank entry point calls this first, so after a peer failure the next call returns STK_ERR_PEER. */
+int stk_comm_poll(stk_ctx* ctx);
 
 /* tuning knobs.  STK_OPT_K1_ALGO: how the cross-rank K1 brings the peers' 16-bit gradients into the SM -- 0 = 16-byte
  * register loads, 1 = bulk-async copies (TMA engine) staged through shared memory (default; +10..20 % bus bandwidth).  Same
  * results either way; fp32 gradients and launches with a local accumulator always take flavour 0.
  * Also settable at context creation through the environment variable STK_K1_ALGO=ldg|bulk. */
 #define STK_OPT_K1_ALGO 1
+/* 2 = multimem (NVLS): multimem.ld_reduce of the owned shard + multimem.st of the result; taken when the gradient and
+ *     output buffers are multicast-bound and there is no local accumulator, otherwise the call falls back to 1 / 0.
+ *     16-bit sums are rounded to the input type by the switch (fp32 accumulation inside it) -- NCCL's NVLS numerics.
+ * STK_OPT_MEM_MODE: 0 = ipc, 1 = vmm (see stk_mem_alloc_shared).  STK_OPT_K1_MAX_BLOCKS: grid bound of the cross-rank
+ * K1 (default: one block per SM); smaller grids leave SMs to a concurrently running backward. */
+#define STK_OPT_MEM_MODE 2
+#define STK_OPT_K1_MAX_BLOCKS 3
+#define STK_OPT_COOP_LAUNCH 4   /* 1 (default): cross-rank kernels use cooperative launches (co-residency enforced) */
 int stk_option_set(stk_ctx* ctx, int key, int value);
+int stk_option_get(stk_ctx* ctx, int key, int* value);
 
 /* launch timing for bench.py's roofline: when enabled, K1 (kind 0), K2 (kind 1) and the accumulate kernel (kind 2) are
  * bracketed by CUDA events on the launch stream; stk_profile_read synchronises those events, returns the summed
@@ -134,6 +167,12 @@ int stk_profile_read(stk_ctx* ctx, int kind, double* ms_total, int* launches);
 int stk_profile_read_k1_device(stk_ctx* ctx, double* ms_total, int* launches, double* ms_zero_tail, void* stream);
 
 /* ---- scaler / step state ------------------------------------------------------------------------------------------- */
+/* One device-resident state (loss scaler, found_inf, grad_norm, step counters, per-step norm accumulators) per optimizer.
+ * State 0 exists from stk_ctx_create.  stk_state_select makes `id` the state that stk_scaler_*, stk_grad_reduce,
+ * stk_grad_norm, stk_grad_scale, stk_optim_step* and stk_step_epilogue read and write until the next select. */
+int stk_state_create(stk_ctx* ctx, int* id_out);
+int stk_state_select(stk_ctx* ctx, int id);
+int stk_state_destroy(stk_ctx* ctx, int id);
 int stk_scaler_set(stk_ctx* ctx, const stk_scaler_state_t* st, void* stream);
 int stk_scaler_get(stk_ctx* ctx, stk_scaler_state_t* st, void* stream); /* synchronises `stream` */
 void* stk_scaler_scale_ptr(stk_ctx* ctx); /* device float*: the live loss scale (for scaler.scale(loss)) */
@@ -152,6 +191,17 @@ int stk_grad_reduce(stk_ctx* ctx, int mode, void* const* grad_ptrs, int grad_dty
                     void* const* out_ptrs, int out_dtype, size_t n, double mul, int norm_kind, double norm_p,
                     unsigned flags, void* stream);
 
+/* Norm / inf pass without a reduce (world == 1, or gradients that were reduced elsewhere): accumulates the norm partial and
+ * the inf/nan flag of x[i] = (float(grad[i]) [+ acc[i]]) * mul * (1/scale) over [0, n) into the selected state and, with
+ * STK_RF_FINAL, finishes them (grad_norm, found_inf).  Reads grad once, writes nothing: stk_optim_step_ex then consumes the
+ * raw bucket directly (no fp32 main-grad round trip through HBM).  Loads keep the bucket L2-resident for that second read. */
+int stk_grad_norm(stk_ctx* ctx, const void* grad, int grad_dtype, const float* acc, size_t n, double mul, int norm_kind,
+                  double norm_p, unsigned flags, void* stream);
+
+/* In-place clip of already reduced fp32 gradients for the stock-optimizer route: grad[i] *= min(max_norm/(norm+1e-6), 1)
+ * (STK_CLIP_NORM, norm from the selected state) or clamp (STK_CLIP_VALUE). */
+int stk_grad_scale(stk_ctx* ctx, float* grad, size_t n, int clip_kind, double clip_max_norm, double clip_value, void* stream);
+
 /* element range [begin, end) of the shard `rank` owns in a bucket of n elements (same partition the kernels use) */
 int stk_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end);
 
@@ -163,12 +213,50 @@ int stk_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end);
 int stk_optim_step(stk_ctx* ctx, const stk_optim_hyper_t* hyper, float* master, float* exp_avg, float* exp_avg_sq,
                    const float* grad, size_t n_local, void* const* lp_ptrs, int lp_world, int lp_dtype, size_t lp_offset,
                    void* stream);
+
+/* Extended form.  Everything stk_optim_step does, plus:
+ *  - raw gradient source (grad_raw = 1): `grad` is the local model-dtype bucket (+ optional fp32 accumulator), scaled by
+ *    grad_mul and 1/loss_scale inside the kernel and ZEROED after it has been read (also on a skipped step); pairs with
+ *    stk_grad_norm -- the world == 1 route: 2 + 30 B/element instead of 8 + 30.
+ *  - segments: the local state [0, n_local) is the concatenation of n_seg pieces; piece k covers local elements
+ *    [seg_local[k], seg_local[k+1]) and global (flat-buffer) elements starting at seg_global[k].  lp_ptrs / raw grads /
+ *    the range table are indexed globally.  n_seg = 0: one piece, global offset lp_offset (the plain call).
+ *  - parameter groups and unused parameters: n_ranges > 0 gives a table over the GLOBAL flat index space; range j ends at
+ *    element range_end[j] (ascending, device memory, multiples of 8) and uses hyper[range_group[j] & 0x7f]; bit 7 set = skip
+ *    the range this step (parameter received no gradient: torch skips it, torch/optim/optimizer.py).  n_ranges = 0: hyper[0]
+ *    everywhere.  With 32-byte peer stores (bf16 parameters, segments on 16-element boundaries) a thread handles two adjacent
+ *    vectors and looks the range up once: ranges must then end on 16-element boundaries. */
+#define STK_MAX_GROUPS 8
+#define STK_MAX_SEGMENTS 64
+typedef struct {
+  const stk_optim_hyper_t* hyper;   /* n_groups entries (clip fields taken from hyper[0]) */
+  int n_groups;
+  float* master; float* exp_avg; float* exp_avg_sq;
+  const void* grad; int grad_dtype;  /* STK_F32 reduced main grads (local indexing) | raw bucket (global indexing) */
+  int grad_raw;
+  const float* acc;                  /* raw route only: fp32 accumulator added to grad (global indexing), may be NULL */
+  double grad_mul;                   /* raw route only */
+  size_t n_local;
+  void* const* lp_ptrs; int lp_world; int lp_dtype; size_t lp_offset;
+  int n_seg; const size_t* seg_local; const size_t* seg_global;   /* host arrays: n_seg + 1 and n_seg entries */
+  int n_ranges; const uint32_t* range_end_vec; const uint8_t* range_group;  /* DEVICE arrays; ends in units of 8 elements */
+  size_t grid_n;   /* cross-rank (lp_world > 1) launches: the LARGEST n_local over the ranks, identical on every rank, so that
+                      every rank launches the same grid (the block barriers pair block b with block b); 0: n_local */
+} stk_optim_args_t;
+int stk_optim_step_ex(stk_ctx* ctx, const stk_optim_args_t* args, void* stream);
+
 /* scaler.update(), opt_steps/skipped_steps bookkeeping, reset of the per-step accumulators */
 int stk_step_epilogue(stk_ctx* ctx, void* stream);
 
 /* ---- small collectives on the signal pads -------------------------------------------------------------------------- */
 /* mean over ranks of *loss_dev (float32/bf16/f16 scalar) -> *out_host (pinned, mapped) ; synchronises `stream` */
 int stk_loss_sync(stk_ctx* ctx, const void* loss_dev, int dtype, double* out_host, void* stream);
+/* The same mean without the host synchronisation: _begin launches the kernel, which writes the mean to a slot of a pinned
+ * ring and returns a ticket; _wait blocks until that launch has finished (no-op if it already has) and returns the value.
+ * At most STK_LOSS_RING tickets may be outstanding (older slots are overwritten). */
+#define STK_LOSS_RING 256
+int stk_loss_sync_begin(stk_ctx* ctx, const void* loss_dev, int dtype, int64_t* ticket_out, void* stream);
+int stk_loss_sync_wait(stk_ctx* ctx, int64_t ticket, double* out_host);
 int stk_barrier(stk_ctx* ctx, void* stream);
 /* every rank copies bytes from ptrs[root] to ptrs[rank] (peer pull) with start/end barriers */
 int stk_bcast(stk_ctx* ctx, void* const* ptrs, size_t bytes, int root, void* stream);

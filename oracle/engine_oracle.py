@@ -41,6 +41,11 @@ class OracleEngine:
     grad_accum: micro-steps per optimizer step
     clip: None | ("norm", max_norm, norm_type) | ("value", clip_value)   (ClipGradNormConfig / ClipGradConfig)
     amp: None | dict(init_scale, growth_factor, backoff_factor, growth_interval)   (AMPConfig, stoke/configs.py:44-65)
+    groups: None | [(parameter indices, per-group optimizer kwargs), ...]   (torch parameter groups)
+
+    A gradient entry may be ``None``: the parameter received no gradient on that rank in that micro-step (an unused
+    parameter); a parameter whose accumulated gradient is ``None`` is skipped by the optimizer, as torch does after
+    ``zero_grad(set_to_none=True)`` (stoke/utils.py:103-106).
     """
 
     def __init__(
@@ -52,12 +57,18 @@ class OracleEngine:
         grad_accum: int = 1,
         clip: Optional[Tuple] = None,
         amp: Optional[Dict] = None,
+        groups: Optional[Sequence[Tuple[Sequence[int], Dict]]] = None,
     ):
         self.world = int(world)
         self.grad_accum = int(grad_accum)
         self.clip = clip
         self.params = [torch.nn.Parameter(p.detach().to(torch.float32).cpu().clone()) for p in params]
-        self.optimizer = optimizer(params=self.params, **optimizer_kwargs)
+        if groups is None:
+            self.optimizer = optimizer(params=self.params, **optimizer_kwargs)
+        else:
+            # torch-style parameter groups: (indices into params, per-group overrides)
+            self.optimizer = optimizer([dict(extra, params=[self.params[i] for i in idx]) for idx, extra in groups],
+                                       **optimizer_kwargs)
         self.scaler = None
         if amp is not None:
             # the reference builds torch.cuda.amp.GradScaler (stoke/fp16.py:733-748); the CPU build of the same class
@@ -89,12 +100,17 @@ class OracleEngine:
         1/grad_accum (stoke/stoke.py:910-911).  AccumulateGrad adds it to ``param.grad`` in fp32."""
         assert len(grads_per_rank) == self.world
         for r in range(self.world):
-            g = [x.detach().to(torch.float32).cpu() for x in grads_per_rank[r]]
+            g = [None if x is None else x.detach().to(torch.float32).cpu() for x in grads_per_rank[r]]
             if self._local[r] is None:
-                self._local[r] = [x.clone() for x in g]
+                self._local[r] = [None if x is None else x.clone() for x in g]
             else:
-                for acc, x in zip(self._local[r], g):
-                    acc.add_(x)
+                for i, x in enumerate(g):
+                    if x is None:
+                        continue
+                    if self._local[r][i] is None:
+                        self._local[r][i] = x.clone()
+                    else:
+                        self._local[r][i].add_(x)
         self._micro += 1
 
     def ready(self) -> bool:
@@ -110,19 +126,21 @@ class OracleEngine:
             red = None
             for r in range(W):
                 g = self._local[r][i]
+                if g is None:
+                    continue
                 g = g / W if W > 1 else g
                 red = g.clone() if red is None else red.add_(g)
-            p.grad = red.reshape(p.shape)
+            p.grad = None if red is None else red.reshape(p.shape)
         stepped = True
         if self.clip is not None:
             if self.scaler is not None:
                 self.scaler.unscale_(self.optimizer)
             if self.clip[0] == "norm":
                 self.last_total_norm = torch.nn.utils.clip_grad_norm_(
-                    self.params, max_norm=self.clip[1], norm_type=self.clip[2]
+                    [p for p in self.params if p.grad is not None], max_norm=self.clip[1], norm_type=self.clip[2]
                 )
             elif self.clip[0] == "value":
-                torch.nn.utils.clip_grad_value_(self.params, clip_value=self.clip[1])
+                torch.nn.utils.clip_grad_value_([p for p in self.params if p.grad is not None], clip_value=self.clip[1])
             else:
                 raise ValueError(self.clip)
         if self.scaler is not None:

@@ -1,9 +1,10 @@
 # -*- coding: utf-8 -*-
 """TEST INFRASTRUCTURE ONLY -- import shim for the unmodified reference (fidelity/stoke).
 
-Only usable in the build container, where ``/root/reference`` exists (it does not travel to the GPU box).
-It is used by ``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/`` and by the CPU tests
-that validate ``oracle/`` against the real reference when it is present.
+Looks for the reference package at ``/root/reference`` (build container) and, failing that, at ``oracle/_ref`` -- the
+verbatim, git-ignored copy that ``oracle/build_ref.py`` makes and that travels to the GPU box with the snapshot.
+It is used by ``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/``, by the CPU tests that validate
+``oracle/`` against the real reference, and by ``bench.py``'s ``--impl reference`` / ``cpu_baseline`` legs.
 
 Why a shim: the reference imports ``horovod``, ``deepspeed`` and ``fairscale`` at module scope
 (/root/reference/stoke/data.py:12, distributed.py:14-18, io_ops.py:12-15, fp16.py:14-15, extensions.py:14-15,
@@ -15,7 +16,10 @@ import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("STOKE_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "stoke")) and os.path.isdir(os.path.join(_HERE, "_ref", "stoke")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
 
 
 def reference_available() -> bool:

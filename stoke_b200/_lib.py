@@ -16,8 +16,9 @@ NORM_NONE, NORM_L2, NORM_INF, NORM_P = 0, 1, 2, 3
 CLIP_NONE, CLIP_NORM, CLIP_VALUE = 0, 1, 2
 OPT_ADAM, OPT_ADAMW, OPT_SGD = 0, 1, 2
 RF_FINAL, RF_ZERO_INPUT, RF_UNSCALE = 1, 2, 4
-OPT_K1_ALGO = 1
-K1_ALGO_LDG, K1_ALGO_BULK = 0, 1
+OPT_K1_ALGO, OPT_MEM_MODE, OPT_K1_MAX_BLOCKS, OPT_COOP_LAUNCH = 1, 2, 3, 4
+K1_ALGO_LDG, K1_ALGO_BULK, K1_ALGO_NVLS = 0, 1, 2
+MAX_GROUPS, MAX_SEGMENTS, LOSS_RING = 8, 64, 256
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_PEER, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 
 
@@ -47,6 +48,16 @@ class OptimHyper(C.Structure):
                 ("clip_max_norm", C.c_double), ("clip_value", C.c_double)]
 
 
+class OptimArgs(C.Structure):
+    _fields_ = [("hyper", C.POINTER(OptimHyper)), ("n_groups", C.c_int), ("master", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("grad", C.c_void_p), ("grad_dtype", C.c_int), ("grad_raw", C.c_int),
+                ("acc", C.c_void_p), ("grad_mul", C.c_double), ("n_local", C.c_size_t),
+                ("lp_ptrs", C.POINTER(C.c_void_p)), ("lp_world", C.c_int), ("lp_dtype", C.c_int), ("lp_offset", C.c_size_t),
+                ("n_seg", C.c_int), ("seg_local", C.POINTER(C.c_size_t)), ("seg_global", C.POINTER(C.c_size_t)),
+                ("n_ranges", C.c_int), ("range_end_vec", C.c_void_p), ("range_group", C.c_void_p),
+                ("grid_n", C.c_size_t)]
+
+
 class SamplerPlan(C.Structure):
     _fields_ = [("n", C.c_int64), ("buckets", C.c_int64), ("batch_size", C.c_int64), ("world", C.c_int64),
                 ("rank", C.c_int64), ("drop_last", C.c_int32), ("allow_bucket_overlap", C.c_int32),
@@ -71,7 +82,14 @@ _SIGNATURES = {
     "stk_comm_local": (C.c_int, [_P, C.c_char_p]),
     "stk_comm_connect": (C.c_int, [_P, C.c_char_p]),
     "stk_comm_check": (C.c_int, [_P, _P]),
+    "stk_comm_poll": (C.c_int, [_P]),
+    "stk_multicast_try_bind": (C.c_int, [_P, _P, _PP]),
+    "stk_multicast_release": (C.c_int, [_P, _P]),
+    "stk_state_create": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "stk_state_select": (C.c_int, [_P, C.c_int]),
+    "stk_state_destroy": (C.c_int, [_P, C.c_int]),
     "stk_option_set": (C.c_int, [_P, C.c_int, C.c_int]),
+    "stk_option_get": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "stk_profile_enable": (C.c_int, [_P, C.c_int]),
     "stk_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "stk_profile_read_k1_device": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), _P]),
@@ -81,11 +99,16 @@ _SIGNATURES = {
     "stk_grad_accumulate": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     "stk_grad_reduce": (C.c_int, [_P, C.c_int, _PP, C.c_int, _PP, _PP, C.c_int, C.c_size_t, C.c_double, C.c_int,
                                   C.c_double, C.c_uint, _P]),
+    "stk_grad_norm": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t, C.c_double, C.c_int, C.c_double, C.c_uint, _P]),
+    "stk_grad_scale": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_double, C.c_double, _P]),
     "stk_shard_range": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "stk_optim_step": (C.c_int, [_P, C.POINTER(OptimHyper), _P, _P, _P, _P, C.c_size_t, _PP, C.c_int, C.c_int,
                                  C.c_size_t, _P]),
+    "stk_optim_step_ex": (C.c_int, [_P, C.POINTER(OptimArgs), _P]),
     "stk_step_epilogue": (C.c_int, [_P, _P]),
     "stk_loss_sync": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
+    "stk_loss_sync_begin": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int64), _P]),
+    "stk_loss_sync_wait": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_double)]),
     "stk_barrier": (C.c_int, [_P, _P]),
     "stk_bcast": (C.c_int, [_P, _PP, C.c_size_t, C.c_int, _P]),
     "stk_randperm": (C.c_int, [C.c_uint64, C.POINTER(C.c_int64), C.c_int, _P]),

@@ -60,9 +60,11 @@ class ClipGradNormConfig:
 
 @_cfg
 class DDPConfig:
-    """Data-parallel settings.  ``bucket_cap_mb``, ``gradient_as_bucket_view``, ``find_unused_parameters`` and
-    ``static_graph`` are accepted for compatibility: the engine keeps gradients in one flat peer-visible bucket (always a
-    bucket view) and reduces after backward, so they have nothing left to tune."""
+    """Data-parallel settings.  ``bucket_cap_mb`` sizes the gradient buckets whose reduce is launched from autograd hooks
+    while backward is still running (reverse registration order, like torch DDP).  ``gradient_as_bucket_view``,
+    ``find_unused_parameters`` and ``static_graph`` are accepted for compatibility: gradients always live in the flat
+    peer-visible buffer (a bucket view), unused parameters are detected by the hooks, buckets not launched by a hook are
+    flushed in order after backward.  ``no_sync=False`` is accepted with a warning (see distributed.py)."""
     local_rank: Optional[int]
     auto_mpi_discovery: bool = False
     convert_to_sync_batch_norm: bool = False

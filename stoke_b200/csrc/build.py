@@ -11,7 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libstoke_b200.so")
-SOURCES = ["ctx.cu", "k1_reduce.cu", "k1_bulk.cu", "k2_optim.cu", "collectives.cu", "sampler.cu"]
+SOURCES = ["ctx.cu", "vmm.cu", "k1_reduce.cu", "k1_bulk.cu", "k1_nvls.cu", "k1_norm.cu", "k2_optim.cu", "collectives.cu",
+           "sampler.cu"]
 HEADERS = ["common.cuh", "ctx.cuh", "k1_common.cuh", os.path.join("..", "..", "include", "stoke_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",

@@ -34,7 +34,7 @@ __global__ void k_loss_sync(const void* loss, double* out_host, PeerPads pads, i
     st_relaxed_sys_f32(&pads.p[peer]->loss_slot[par][rank], mine);
     __threadfence_system();
     st_release_sys(&pads.p[peer]->aux_flag[1][rank], epoch);
-    wait_flag(&pads.p[rank]->aux_flag[1][peer], epoch, &pads.p[rank]->error);
+    wait_flag(&pads.p[rank]->aux_flag[1][peer], epoch, pads.p[rank]);
     s_val[peer] = ld_relaxed_sys_f32(&pads.p[rank]->loss_slot[par][peer]);
   }
   __syncthreads();
@@ -52,7 +52,7 @@ __global__ void k_barrier(PeerPads pads, int rank, int world, uint32_t epoch) {
     const int peer = threadIdx.x;
     __threadfence_system();
     st_release_sys(&pads.p[peer]->aux_flag[2][rank], epoch);
-    wait_flag(&pads.p[rank]->aux_flag[2][peer], epoch, &pads.p[rank]->error);
+    wait_flag(&pads.p[rank]->aux_flag[2][peer], epoch, pads.p[rank]);
   }
 }
 
@@ -60,7 +60,8 @@ __global__ void k_barrier(PeerPads pads, int rank, int world, uint32_t epoch) {
 __global__ void __launch_bounds__(512) k_bcast_pull(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec16,
                                                      size_t tail_bytes, PeerPads pads, int rank, int world, int is_root,
                                                      uint32_t epoch) {
-  block_barrier_all_ranks(pads, rank, world, 0, epoch);  // root's data is complete (stream order on the root)
+  // root's data is complete (stream order on the root); a missing peer: give up (error word set)
+  if (!block_barrier_all_ranks(pads, rank, world, 0, epoch)) return;
   if (!is_root) {
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec16; i += stride) dst[i] = ld_stream16(src + i);
@@ -79,23 +80,65 @@ using namespace stk;
 
 extern "C" {
 
-int stk_loss_sync(stk_ctx* c, const void* loss_dev, int dtype, double* out_host, void* stream) {
-  STK_REQUIRE(c, c && loss_dev && out_host, "stk_loss_sync: NULL argument");
-  if (c->world > 1 && !c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_loss_sync before stk_comm_connect");
-  std::lock_guard<std::mutex> lk(c->mu);
-  DeviceGuard g(c->device);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+static int launch_loss_sync(stk_ctx* c, const void* loss_dev, int dtype, double* dst, cudaStream_t s) {
   uint32_t epoch = ++c->aux_epoch[1];
-  double* dst = c->host_scratch_dev;  // slot 0 of the pinned, mapped scratch
   switch (dtype) {
     case STK_F32: k_loss_sync<STK_F32><<<1, 32, 0, s>>>(loss_dev, dst, c->pads, c->rank, c->world, epoch); break;
     case STK_BF16: k_loss_sync<STK_BF16><<<1, 32, 0, s>>>(loss_dev, dst, c->pads, c->rank, c->world, epoch); break;
     case STK_F16: k_loss_sync<STK_F16><<<1, 32, 0, s>>>(loss_dev, dst, c->pads, c->rank, c->world, epoch); break;
-    default: return stk_fail(c, STK_ERR_INVALID, "stk_loss_sync: bad dtype");
+    default: --c->aux_epoch[1]; return stk_fail(c, STK_ERR_INVALID, "stk_loss_sync: bad dtype");
   }
   STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
+}
+
+int stk_loss_sync(stk_ctx* c, const void* loss_dev, int dtype, double* out_host, void* stream) {
+  STK_REQUIRE(c, c && loss_dev && out_host, "stk_loss_sync: NULL argument");
+  if (c->world > 1 && !c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_loss_sync before stk_comm_connect");
+  STK_POLL(c);
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = launch_loss_sync(c, loss_dev, dtype, c->host_scratch_dev /* slot 0 of the pinned, mapped scratch */, s);
+  if (rc != STK_OK) return rc;
   STK_CUDA(c, cudaStreamSynchronize(s));
+  STK_POLL(c);  // this call synchronised: a peer that never arrived is reported here, not one step later
   *out_host = c->host_scratch[0];
+  return STK_OK;
+}
+
+int stk_loss_sync_begin(stk_ctx* c, const void* loss_dev, int dtype, int64_t* ticket_out, void* stream) {
+  STK_REQUIRE(c, c && loss_dev && ticket_out, "stk_loss_sync_begin: NULL argument");
+  if (c->world > 1 && !c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_loss_sync_begin before stk_comm_connect");
+  STK_POLL(c);
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t ticket = c->loss_ticket;
+  const int slot = (int)(ticket % STK_LOSS_RING);
+  if (!c->loss_events[slot]) STK_CUDA(c, cudaEventCreateWithFlags(&c->loss_events[slot], cudaEventDisableTiming));
+  int rc = launch_loss_sync(c, loss_dev, dtype, c->loss_ring_dev + slot, s);
+  if (rc != STK_OK) return rc;
+  STK_CUDA(c, cudaEventRecord(c->loss_events[slot], s));
+  c->loss_ticket = ticket + 1;
+  *ticket_out = ticket;
+  return STK_OK;
+}
+
+int stk_loss_sync_wait(stk_ctx* c, int64_t ticket, double* out_host) {
+  STK_REQUIRE(c, c && out_host, "stk_loss_sync_wait: NULL argument");
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    STK_REQUIRE(c, ticket >= 0 && ticket < c->loss_ticket, "stk_loss_sync_wait: no such ticket");
+    if (c->loss_ticket - ticket > STK_LOSS_RING)
+      return stk_fail(c, STK_ERR_STATE, "stk_loss_sync_wait: the ticket's slot has been overwritten (more than STK_LOSS_RING outstanding)");
+    ev = c->loss_events[ticket % STK_LOSS_RING];
+  }
+  DeviceGuard g(c->device);
+  STK_CUDA(c, cudaEventSynchronize(ev));
+  STK_POLL(c);
+  *out_host = c->loss_ring[ticket % STK_LOSS_RING];
   return STK_OK;
 }
 
@@ -103,12 +146,14 @@ int stk_barrier(stk_ctx* c, void* stream) {
   STK_REQUIRE(c, c != nullptr, "stk_barrier: NULL ctx");
   if (c->world == 1) return STK_OK;
   if (!c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_barrier before stk_comm_connect");
+  STK_POLL(c);
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   k_barrier<<<1, 32, 0, s>>>(c->pads, c->rank, c->world, ++c->aux_epoch[2]);
   STK_CUDA(c, cudaGetLastError());
   STK_CUDA(c, cudaStreamSynchronize(s));
+  STK_POLL(c);
   return STK_OK;
 }
 
@@ -117,6 +162,7 @@ int stk_bcast(stk_ctx* c, void* const* ptrs, size_t bytes, int root, void* strea
   STK_REQUIRE(c, root >= 0 && root < c->world, "stk_bcast: bad root");
   if (c->world == 1 || bytes == 0) return STK_OK;
   if (!c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_bcast before stk_comm_connect");
+  STK_POLL(c);
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -130,7 +176,7 @@ int stk_bcast(stk_ctx* c, void* const* ptrs, size_t bytes, int root, void* strea
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = c->coop_launch ? 1 : 0;
   const uint4* src = reinterpret_cast<const uint4*>(ptrs[root]);
   uint4* dst = reinterpret_cast<uint4*>(ptrs[c->rank]);
   uint32_t epoch = ++c->blk_epoch;

@@ -11,8 +11,8 @@ namespace stk {
 
 constexpr int kMaxWorld = STK_MAX_WORLD;
 constexpr int kMaxBlocks = 1024;
-constexpr int kMaxReduceBlocks = 256;        // grid bound of the cross-rank K1 (one block per SM)             // upper bound on the grid of any cross-rank kernel (flag slots per peer)
-constexpr uint64_t kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s: a dead peer becomes an error, not a hang
+constexpr int kMaxReduceBlocks = 512;        // grid bound of the cross-rank K1 (one block per SM)             // upper bound on the grid of any cross-rank kernel (flag slots per peer)
+constexpr uint64_t kDefaultSpinTimeoutNs = 600ull * 1000ull * 1000ull * 1000ull;  // 10 min (STK_SPIN_TIMEOUT_S): a dead peer becomes an error, not a hang
 
 // ---- signal pad layout (one per rank, peer-mapped) ------------------------------------------------------------------
 // All flags are monotonically increasing epochs written by the peer (st.release.sys) and polled locally
@@ -28,6 +28,10 @@ struct SignalPad {
   RankScalars blk_scal[kMaxWorld][kMaxReduceBlocks];  // [r][b]: norm partial / inf flag of rank r's K1 block b
   float loss_slot[2][kMaxWorld];                // double-buffered by call parity
   uint32_t error;                               // non-zero: a spin bound was hit on this rank
+  // ---- local-only fields (peers never touch them) ----
+  uint32_t pad0_;
+  uint64_t timeout_ns;                          // spin bound of wait_flag
+  uint32_t* host_err;                           // mapped pinned host word mirrored from `error` (polled by the host without a sync)
 };
 
 struct PeerPads {
@@ -68,16 +72,22 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
-// Wait until *flag >= epoch (epochs only grow).  Bounded: on timeout sets pad->error and returns false.
-__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* err) {
+// Wait until *flag >= epoch (epochs only grow).  Bounded: on timeout (or when this rank already failed) raises the local
+// pad's error word AND its mirror in mapped host memory -- which every host entry point polls, so the next library call
+// returns STK_ERR_PEER -- and returns false; callers abandon the kernel's data phase instead of consuming garbage.
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, SignalPad* mine) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
     if ((++spins & 0x3ff) == 0) {
       uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > kSpinTimeoutNs) {
-        st_relaxed_sys_u32(err, 1u);
+      else if (now - t0 > mine->timeout_ns || ld_relaxed_sys_u32(&mine->error) != 0) {
+        st_relaxed_sys_u32(&mine->error, 1u);
+        if (mine->host_err) {
+          *reinterpret_cast<volatile uint32_t*>(mine->host_err) = 1u;
+          __threadfence_system();
+        }
         return false;
       }
     }
@@ -86,17 +96,19 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, 
 }
 
 // Block-to-block barrier across ranks: block b of every rank arrives, then block b of every rank proceeds.
-// Call with all threads of the block.  `which` selects the start (0) or end (1) flag row.
-__device__ __forceinline__ void block_barrier_all_ranks(const PeerPads& pads, int rank, int world, int which,
+// Call with all threads of the block.  `which` selects the start (0) or end (1) flag row.  Returns false (to every thread
+// of the block) when a peer did not arrive within the spin bound.
+__device__ __forceinline__ bool block_barrier_all_ranks(const PeerPads& pads, int rank, int world, int which,
                                                         uint32_t epoch) {
   __syncthreads();
+  int ok = 1;
   if (threadIdx.x < (unsigned)world) {
     const int peer = threadIdx.x;
     __threadfence_system();
     st_release_sys(&pads.p[peer]->blk_flag[which][blockIdx.x][rank], epoch);
-    wait_flag(&pads.p[rank]->blk_flag[which][blockIdx.x][peer], epoch, &pads.p[rank]->error);
+    ok = wait_flag(&pads.p[rank]->blk_flag[which][blockIdx.x][peer], epoch, pads.p[rank]) ? 1 : 0;
   }
-  __syncthreads();
+  return __syncthreads_and(ok) != 0;
 }
 
 // ---- 16-byte vector access -------------------------------------------------------------------------------------------
@@ -150,6 +162,38 @@ __device__ __forceinline__ float f16lo(uint32_t u) {
 __device__ __forceinline__ float f16hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
 
 __device__ __forceinline__ bool finitef(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
+
+// ---- NVLS: multimem accesses on a multicast mapping (one address = the same offset in every rank's buffer; the NVSwitch
+// reduces the W copies on a load and replicates a store).  SASS: LDGMC.E.ADD.* / STG on the multicast address. -------------
+__device__ __forceinline__ uint4 mm_ld_reduce_bf16x8(const void* mc) {  // sum over ranks of 8 bf16, fp32 accumulation
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 mm_ld_reduce_f16x8(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 mm_ld_reduce_f32x4(const void* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st16(void* mc, const uint4& v) {  // 16 bytes replicated to every rank
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
 
 // ---- block reductions (fixed tree -> deterministic) --------------------------------------------------------------------
 template <bool kMax>

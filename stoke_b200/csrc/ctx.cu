@@ -36,7 +36,7 @@ int stk_grow_partials(stk_ctx* c, size_t blocks, cudaStream_t s) {
 
 extern "C" {
 
-int stk_version(void) { return 100; }
+int stk_version(void) { return 200; }
 
 const char* stk_last_error(stk_ctx* ctx) {
   if (ctx && !ctx->err.empty()) return ctx->err.c_str();
@@ -60,24 +60,40 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   c->world = world;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (const char* algo = std::getenv("STK_K1_ALGO")) c->k1_algo = (std::strcmp(algo, "bulk") == 0) ? 1 : 0;
+  if (const char* algo = std::getenv("STK_K1_ALGO"))
+    c->k1_algo = (std::strcmp(algo, "nvls") == 0) ? 2 : (std::strcmp(algo, "bulk") == 0) ? 1 : 0;
+  if (const char* v = std::getenv("STK_K1_MAX_BLOCKS")) c->k1_max_blocks = std::atoi(v);
+  if (const char* v = std::getenv("STK_COOP_LAUNCH")) c->coop_launch = std::atoi(v) != 0;
+  // memory back end: VMM (needed for NVLS multicast) when there are peers and the driver supports it
+  bool mc = false;
+  const bool vmm = stk_vmm_available(device, &mc);
+  c->multicast_ok = vmm && mc && world > 1;
+  c->mem_mode = (vmm && world > 1) ? 1 : 0;
+  if (const char* m = std::getenv("STK_MEM")) {
+    if (std::strcmp(m, "ipc") == 0) c->mem_mode = 0;
+    else if (std::strcmp(m, "vmm") == 0 && vmm) c->mem_mode = 1;
+  }
+  if (c->mem_mode == 0) c->multicast_ok = false;
   cudaError_t e;
-  if ((e = cudaMalloc(&c->scaler_dev, sizeof(stk_scaler_state_t))) != cudaSuccess ||
-      (e = cudaMalloc(&c->accum_dev, sizeof(StepAccum))) != cudaSuccess ||
-      (e = cudaMalloc(&c->prof_ns_dev, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+  if ((e = cudaMalloc(&c->prof_ns_dev, 4 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMemset(c->prof_ns_dev, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaHostAlloc(&c->host_scratch, sizeof(double) * 16, cudaHostAllocMapped)) != cudaSuccess ||
-      (e = cudaHostGetDevicePointer(&c->host_scratch_dev, c->host_scratch, 0)) != cudaSuccess) {
+      (e = cudaHostGetDevicePointer(&c->host_scratch_dev, c->host_scratch, 0)) != cudaSuccess ||
+      (e = cudaHostAlloc(&c->loss_ring, sizeof(double) * STK_LOSS_RING, cudaHostAllocMapped)) != cudaSuccess ||
+      (e = cudaHostGetDevicePointer(&c->loss_ring_dev, c->loss_ring, 0)) != cudaSuccess) {
     delete c;
     return stk_fail(nullptr, STK_ERR_CUDA, std::string("stk_ctx_create: ") + cudaGetErrorString(e));
   }
-  stk_scaler_state_t st{};
-  st.scale = 1.f;
-  st.growth_factor = 2.f;
-  st.backoff_factor = 0.5f;
-  st.growth_interval = 2000;
-  cudaMemcpy(c->scaler_dev, &st, sizeof(st), cudaMemcpyHostToDevice);
-  cudaMemset(c->accum_dev, 0, sizeof(StepAccum));
+  std::memset(c->host_scratch, 0, sizeof(double) * 16);
+  std::memset(c->loss_ring, 0, sizeof(double) * STK_LOSS_RING);
+  {
+    int id = -1;
+    if (stk_state_create(c, &id) != STK_OK || id != 0) {
+      delete c;
+      return STK_ERR_CUDA;
+    }
+    stk_state_select(c, 0);
+  }
   if (stk_grow_partials(c, stk::kMaxBlocks, nullptr) != STK_OK) {
     delete c;
     return STK_ERR_CUDA;
@@ -92,17 +108,28 @@ int stk_ctx_destroy(stk_ctx* c) {
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
   for (auto& kv : c->shared) {
+    if (kv.second.vmm) {
+      stk_vmm_free(c, kv.first, kv.second);
+      continue;
+    }
     if (kv.second.opened)
       for (int r = 0; r < c->world; ++r)
         if (r != c->rank && kv.second.peers[r]) cudaIpcCloseMemHandle(kv.second.peers[r]);
     cudaFree(kv.first);
   }
+  c->shared.clear();
+  stk_vmm_ctx_shutdown(c);
   if (c->comm_ready)
     for (int r = 0; r < c->world; ++r)
       if (r != c->rank && c->pads.p[r]) cudaIpcCloseMemHandle(c->pads.p[r]);
   if (c->pad_local) cudaFree(c->pad_local);
-  cudaFree(c->scaler_dev);
-  cudaFree(c->accum_dev);
+  for (auto& st : c->states) {
+    if (st.scaler_dev) cudaFree(st.scaler_dev);
+    if (st.accum_dev) cudaFree(st.accum_dev);
+  }
+  for (auto& ev : c->loss_events)
+    if (ev) cudaEventDestroy(ev);
+  if (c->loss_ring) cudaFreeHost(c->loss_ring);
   cudaFree(c->blk_partial_dev);
   cudaFree(c->grp_partial_dev);
   cudaFree(c->grp_count_dev);
@@ -124,7 +151,7 @@ int stk_caps(stk_ctx* c, stk_caps_t* out) {
   out->world = c->world;
   out->device = c->device;
   out->peer_access = (c->world == 1) || c->comm_ready;
-  out->multicast = 0;
+  out->multicast = c->multicast_ok ? 1 : 0;
   out->hbm_bytes = prop.totalGlobalMem;
   return STK_OK;
 }
@@ -136,6 +163,7 @@ int stk_mem_alloc_shared(stk_ctx* c, size_t bytes, void** local_ptr, unsigned ch
   static_assert(sizeof(cudaIpcMemHandle_t) == STK_IPC_HANDLE_BYTES, "IPC handle size");
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
+  if (c->mem_mode == 1 && c->world > 1) return stk_vmm_alloc(c, bytes, local_ptr, handle_out);
   void* p = nullptr;
   size_t rounded = (bytes + 255) & ~size_t(255);
   STK_CUDA(c, cudaMalloc(&p, rounded));
@@ -152,8 +180,6 @@ int stk_mem_alloc_shared(stk_ctx* c, size_t bytes, void** local_ptr, unsigned ch
   }
   stk_ctx::Shared s{};
   s.bytes = rounded;
-  s.opened = false;
-  for (int r = 0; r < STK_MAX_WORLD; ++r) s.peers[r] = nullptr;
   s.peers[c->rank] = p;
   c->shared[p] = s;
   *local_ptr = p;
@@ -166,7 +192,11 @@ int stk_mem_open_peers(stk_ctx* c, void* local_ptr, const unsigned char* handles
   auto it = c->shared.find(local_ptr);
   STK_REQUIRE(c, it != c->shared.end(), "stk_mem_open_peers: pointer was not allocated by stk_mem_alloc_shared");
   DeviceGuard g(c->device);
-  if (!it->second.opened && c->world > 1) {
+  if (!it->second.opened && c->world > 1 && it->second.vmm) {
+    STK_REQUIRE(c, handles != nullptr, "stk_mem_open_peers: handles is NULL");
+    int rc = stk_vmm_open(c, it->second, handles);
+    if (rc != STK_OK) return rc;
+  } else if (!it->second.opened && c->world > 1) {
     STK_REQUIRE(c, handles != nullptr, "stk_mem_open_peers: handles is NULL");
     for (int r = 0; r < c->world; ++r) {
       if (r == c->rank) continue;
@@ -189,11 +219,42 @@ int stk_mem_free_shared(stk_ctx* c, void* local_ptr) {
   auto it = c->shared.find(local_ptr);
   STK_REQUIRE(c, it != c->shared.end(), "stk_mem_free_shared: unknown pointer");
   DeviceGuard g(c->device);
-  if (it->second.opened)
-    for (int r = 0; r < c->world; ++r)
-      if (r != c->rank && it->second.peers[r]) cudaIpcCloseMemHandle(it->second.peers[r]);
-  cudaFree(local_ptr);
+  cudaDeviceSynchronize();  // no kernel of this process may still be using the mapping
+  if (it->second.vmm) {
+    stk_vmm_free(c, local_ptr, it->second);
+  } else {
+    if (it->second.opened)
+      for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && it->second.peers[r]) cudaIpcCloseMemHandle(it->second.peers[r]);
+    cudaFree(local_ptr);
+  }
   c->shared.erase(it);
+  return STK_OK;
+}
+
+int stk_multicast_try_bind(stk_ctx* c, void* local_ptr, void** mc_ptr_out) {
+  STK_REQUIRE(c, c && local_ptr && mc_ptr_out, "stk_multicast_try_bind: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->shared.find(local_ptr);
+  STK_REQUIRE(c, it != c->shared.end(), "stk_multicast_try_bind: pointer was not allocated by stk_mem_alloc_shared");
+  *mc_ptr_out = nullptr;
+  if (!c->multicast_ok || !it->second.vmm || !it->second.opened)
+    return stk_fail(c, STK_ERR_UNSUPPORTED, "multicast is not available for this buffer (no NVLS support, ipc memory mode, or peers not opened)");
+  DeviceGuard g(c->device);
+  int rc = stk_vmm_mc_bind(c, it->second);
+  if (rc != STK_OK) return rc;
+  *mc_ptr_out = it->second.mc_ptr;
+  return STK_OK;
+}
+
+int stk_multicast_release(stk_ctx* c, void* local_ptr) {
+  STK_REQUIRE(c, c && local_ptr, "stk_multicast_release: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->shared.find(local_ptr);
+  STK_REQUIRE(c, it != c->shared.end(), "stk_multicast_release: unknown pointer");
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  if (it->second.vmm) stk_vmm_mc_release(c, it->second);
   return STK_OK;
 }
 
@@ -205,6 +266,15 @@ int stk_comm_local(stk_ctx* c, unsigned char handle_out[STK_IPC_HANDLE_BYTES]) {
   if (!c->pad_local) {
     STK_CUDA(c, cudaMalloc(&c->pad_local, sizeof(stk::SignalPad)));
     STK_CUDA(c, cudaMemset(c->pad_local, 0, sizeof(stk::SignalPad)));
+    // local-only fields: the spin bound and the error word's mirror in mapped host memory
+    uint64_t timeout = stk::kDefaultSpinTimeoutNs;
+    if (const char* t = std::getenv("STK_SPIN_TIMEOUT_S")) {
+      double sec = std::atof(t);
+      if (sec > 0) timeout = (uint64_t)(sec * 1e9);
+    }
+    uint32_t* herr = reinterpret_cast<uint32_t*>(c->host_scratch_dev + 12);
+    STK_CUDA(c, cudaMemcpy(&c->pad_local->timeout_ns, &timeout, sizeof(timeout), cudaMemcpyHostToDevice));
+    STK_CUDA(c, cudaMemcpy(&c->pad_local->host_err, &herr, sizeof(herr), cudaMemcpyHostToDevice));
     STK_CUDA(c, cudaDeviceSynchronize());
   }
   std::memset(handle_out, 0, STK_IPC_HANDLE_BYTES);
@@ -246,7 +316,71 @@ int stk_comm_check(stk_ctx* c, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   STK_CUDA(c, cudaMemcpyAsync(&err, &c->pad_local->error, sizeof(err), cudaMemcpyDeviceToHost, s));
   STK_CUDA(c, cudaStreamSynchronize(s));
-  if (err) return stk_fail(c, STK_ERR_PEER, "a peer rank did not arrive within the spin bound (dead or out-of-order rank)");
+  if (err || *c->host_err() != 0)
+    return stk_fail(c, STK_ERR_PEER, "a peer rank did not arrive within the spin bound (dead or out-of-order rank)");
+  return STK_OK;
+}
+
+int stk_comm_poll(stk_ctx* c) {
+  STK_REQUIRE(c, c != nullptr, "stk_comm_poll: NULL ctx");
+  STK_POLL(c);
+  return STK_OK;
+}
+
+// ---- per-optimizer state ---------------------------------------------------------------------------------------------
+int stk_state_create(stk_ctx* c, int* id_out) {
+  STK_REQUIRE(c, c && id_out, "stk_state_create: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  StepState st;
+  STK_CUDA(c, cudaMalloc(&st.scaler_dev, sizeof(stk_scaler_state_t)));
+  STK_CUDA(c, cudaMalloc(&st.accum_dev, sizeof(StepAccum)));
+  stk_scaler_state_t init{};
+  init.scale = 1.f;
+  init.growth_factor = 2.f;
+  init.backoff_factor = 0.5f;
+  init.growth_interval = 2000;
+  STK_CUDA(c, cudaMemcpy(st.scaler_dev, &init, sizeof(init), cudaMemcpyHostToDevice));
+  STK_CUDA(c, cudaMemset(st.accum_dev, 0, sizeof(StepAccum)));
+  int id = -1;
+  for (size_t i = 0; i < c->states.size(); ++i)
+    if (!c->states[i].scaler_dev) {
+      id = (int)i;
+      break;
+    }
+  if (id < 0) {
+    id = (int)c->states.size();
+    c->states.emplace_back();
+  }
+  c->states[id] = st;
+  *id_out = id;
+  return STK_OK;
+}
+
+int stk_state_select(stk_ctx* c, int id) {
+  STK_REQUIRE(c, c != nullptr, "stk_state_select: NULL ctx");
+  std::lock_guard<std::mutex> lk(c->mu);
+  STK_REQUIRE(c, id >= 0 && id < (int)c->states.size() && c->states[id].scaler_dev, "stk_state_select: no such state");
+  c->cur_state = id;
+  c->scaler_dev = c->states[id].scaler_dev;
+  c->accum_dev = c->states[id].accum_dev;
+  return STK_OK;
+}
+
+int stk_state_destroy(stk_ctx* c, int id) {
+  STK_REQUIRE(c, c != nullptr, "stk_state_destroy: NULL ctx");
+  std::lock_guard<std::mutex> lk(c->mu);
+  STK_REQUIRE(c, id > 0 && id < (int)c->states.size() && c->states[id].scaler_dev, "stk_state_destroy: no such state (state 0 lives with the context)");
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  cudaFree(c->states[id].scaler_dev);
+  cudaFree(c->states[id].accum_dev);
+  c->states[id] = StepState{};
+  if (c->cur_state == id) {
+    c->cur_state = 0;
+    c->scaler_dev = c->states[0].scaler_dev;
+    c->accum_dev = c->states[0].accum_dev;
+  }
   return STK_OK;
 }
 
@@ -280,11 +414,37 @@ int stk_option_set(stk_ctx* c, int key, int value) {
   std::lock_guard<std::mutex> lk(c->mu);
   switch (key) {
     case STK_OPT_K1_ALGO:
-      STK_REQUIRE(c, value == 0 || value == 1, "stk_option_set: K1 algo must be 0 (ldg) or 1 (bulk)");
+      STK_REQUIRE(c, value >= 0 && value <= 2, "stk_option_set: K1 algo must be 0 (ldg), 1 (bulk) or 2 (nvls)");
       c->k1_algo = value;
+      return STK_OK;
+    case STK_OPT_MEM_MODE:
+      STK_REQUIRE(c, value == 0 || value == 1, "stk_option_set: memory mode must be 0 (ipc) or 1 (vmm)");
+      if (value == 1 && !stk_vmm_available(c->device, nullptr))
+        return stk_fail(c, STK_ERR_UNSUPPORTED, "stk_option_set: the driver / device has no VMM + POSIX descriptor support");
+      c->mem_mode = value;
+      if (value == 0) c->multicast_ok = false;
+      return STK_OK;
+    case STK_OPT_K1_MAX_BLOCKS:
+      STK_REQUIRE(c, value >= 0 && value <= stk::kMaxReduceBlocks, "stk_option_set: K1 max blocks out of range");
+      c->k1_max_blocks = value;
+      return STK_OK;
+    case STK_OPT_COOP_LAUNCH:
+      c->coop_launch = value != 0;
       return STK_OK;
     default:
       return stk_fail(c, STK_ERR_INVALID, "stk_option_set: unknown key");
+  }
+}
+
+int stk_option_get(stk_ctx* c, int key, int* value) {
+  STK_REQUIRE(c, c && value, "stk_option_get: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  switch (key) {
+    case STK_OPT_K1_ALGO: *value = c->k1_algo; return STK_OK;
+    case STK_OPT_MEM_MODE: *value = c->mem_mode; return STK_OK;
+    case STK_OPT_K1_MAX_BLOCKS: *value = c->k1_max_blocks; return STK_OK;
+    case STK_OPT_COOP_LAUNCH: *value = c->coop_launch; return STK_OK;
+    default: return stk_fail(c, STK_ERR_INVALID, "stk_option_get: unknown key");
   }
 }
 
@@ -296,7 +456,7 @@ int stk_profile_enable(stk_ctx* c, int on) {
 }
 
 int stk_profile_read(stk_ctx* c, int kind, double* ms_total, int* launches) {
-  STK_REQUIRE(c, c && ms_total && launches && kind >= 0 && kind < 3, "stk_profile_read: bad argument");
+  STK_REQUIRE(c, c && ms_total && launches && kind >= 0 && kind < 4, "stk_profile_read: bad argument");
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   double tot = 0.0;
@@ -333,9 +493,10 @@ int stk_profile_read_k1_device(stk_ctx* c, double* ms_total, int* launches, doub
 
 int stk_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end) {
   if (!begin || !end || world < 1 || rank < 0 || rank >= world) return stk_fail(nullptr, STK_ERR_INVALID, "stk_shard_range: bad argument");
-  // shards are multiples of 8 elements (16 B of bf16 / 32 B of fp32) so every vector access stays aligned
+  // shards are multiples of 16 elements (32 B of bf16: the sharded optimizer step pushes 32-byte sectors to its peers)
   size_t vecs = (n + 7) / 8;
   size_t per = (vecs + world - 1) / world;
+  per += per & 1;
   size_t b = per * rank * 8, e = per * (rank + 1) * 8;
   if (b > n) b = n;
   if (e > n) e = n;

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kBulkThreads, 1) k_grad_reduce_bulk(const Redu
     for (int s = 0; s < nstage; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  block_barrier_all_ranks(p.pads, p.rank, W, 0, p.epoch);  // peers' gradients are complete (and barriers are initialised)
+  // peers' gradients are complete (and barriers are initialised); a missing peer: give up, the error word is set
+  if (!block_barrier_all_ranks(p.pads, p.rank, W, 0, p.epoch)) return;
   unsigned long long t_begin = 0;
   if (p.prof_ns && blockIdx.x == 0 && tid == 0) t_begin = globaltimer_ns();
 
@@ -156,10 +157,7 @@ static cudaError_t launch_bulk_t(stk_ctx* c, const ReduceParams& p, int grid, cu
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  coop_attr(c, cfg, attr);
   ProfScope prof(c, 0, s);
 #define STK_BULK(WT)                                                                                              \
   {                                                                                                               \

@@ -10,6 +10,8 @@ struct ReduceParams {
   PtrTable grad;      // W peer pointers to the gradient bucket
   PtrTable acc;       // W peer pointers to the fp32 local accumulators (p[0] == nullptr: none)
   PtrTable out;       // W peer pointers to the main-grad bucket
+  const void* grad_mc;  // multicast mapping of the gradient bucket (multimem flavour only)
+  void* out_mc;         // multicast mapping of the output bucket (multimem flavour, all-reduce mode)
   PeerPads pads;
   stk_scaler_state_t* scaler;
   StepAccum* accum;
@@ -117,7 +119,9 @@ __device__ __forceinline__ void reduce_tail(const ReduceParams& p, float part, b
       st_relaxed_sys_f32(&slot->norm_partial, blk);
       st_relaxed_sys_u32(&slot->found_inf, any_bad);
     }
-    block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch);
+    // a peer that never arrives: give up (error word is set, the host raises STK_ERR_PEER at its next call); nothing is
+    // zeroed or finalised on top of an incomplete exchange
+    if (!block_barrier_all_ranks(p.pads, p.rank, W, 1, p.epoch)) return;
   }
   // end of the NVLink data phase (all peer reads and peer writes of this block are complete on every rank)
   unsigned long long t_data_end = 0;
@@ -261,5 +265,14 @@ __device__ __forceinline__ void reduce_tail(const ReduceParams& p, float part, b
 
 // k1_bulk.cu: shared-memory / bulk-async flavour for cross-rank 16-bit buckets; cudaErrorNotSupported -> use k_grad_reduce
 cudaError_t launch_reduce_bulk(stk_ctx* c, const ReduceParams& p, int grad_dtype, int out_dtype, int grid, cudaStream_t s);
+// k1_nvls.cu: multimem (NVSwitch in-network reduction) flavour; cudaErrorNotSupported -> next flavour
+cudaError_t launch_reduce_nvls(stk_ctx* c, const ReduceParams& p, int grad_dtype, int out_dtype, int grid, cudaStream_t s);
+
+inline void coop_attr(stk_ctx* c, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = c->coop_launch ? 1 : 0;
+}
 
 }  // namespace stk

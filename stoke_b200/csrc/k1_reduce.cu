@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(W_T == 1 ? 256 : 512, W_T == 1 ? 6 : 1) k_grad
   const bool has_acc = p.acc.p[0] != nullptr;
   const bool zero_in = (p.flags & STK_RF_ZERO_INPUT) && W == 1;
 
-  if (W > 1) block_barrier_all_ranks(p.pads, p.rank, W, 0, p.epoch);
+  if (W > 1 && !block_barrier_all_ranks(p.pads, p.rank, W, 0, p.epoch)) return;  // peer missing: error word set
   // device-side timing of the data phase (after the start barrier = after the slowest rank has arrived, up to the end
   // barrier): the NVLink time of this launch without the cross-rank launch skew that host-side events include
   unsigned long long t_begin = 0;
@@ -144,10 +144,8 @@ static cudaError_t launch_reduce(stk_ctx* c, const ReduceParams& p, int grid, bo
   cfg.blockDim = dim3(p.world == 1 ? 256 : 512);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = coop ? 1 : 0;
+  coop_attr(c, cfg, attr);
+  if (!coop) cfg.numAttrs = 0;
   ProfScope prof(c, 0, s);
   switch (p.world) {
     case 1: return cudaLaunchKernelEx(&cfg, k_grad_reduce<IN_DT, OUT_DT, 1>, p);
@@ -193,6 +191,7 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   STK_REQUIRE(c, out_dtype == STK_F32 || out_dtype == STK_BF16, "stk_grad_reduce: out dtype must be f32 or bf16");
   STK_REQUIRE(c, norm_kind >= STK_NORM_NONE && norm_kind <= STK_NORM_P, "stk_grad_reduce: bad norm kind");
   if (c->world > 1 && !c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_grad_reduce before stk_comm_connect");
+  STK_POLL(c);
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -218,6 +217,7 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   p.vec_end = (e + 7) / 8;
   p.vec_total = (n + 7) / 8;
   p.vec_per_shard = ((n + 7) / 8 + W - 1) / W;
+  p.vec_per_shard += p.vec_per_shard & 1;  // same partition as stk_shard_range
   p.mul = (float)mul;
   p.norm_p = (float)norm_p;
   p.rank = c->rank;
@@ -230,12 +230,13 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
 
   // grid: identical on every rank (depends on n and W only).  Cross-rank kernels spin on peers, so every block must be
   // resident: one 512-thread block per SM, cooperative launch.
-  const size_t nvec_shard = ((n + 7) / 8 + W - 1) / W;
+  const size_t nvec_shard = p.vec_per_shard;
   const int U = W == 1 ? 2 : (W == 2 ? 2 : 1);
   const size_t threads = W == 1 ? 256 : 512;
   size_t want = (nvec_shard + threads * U - 1) / (threads * U);
   int grid;
-  if (W > 1) grid = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)c->sm_count));
+  const size_t cap = c->k1_max_blocks > 0 ? (size_t)std::min(c->k1_max_blocks, c->sm_count) : (size_t)c->sm_count;
+  if (W > 1) grid = (int)std::max<size_t>(1, std::min<size_t>(want, cap));
   else grid = (int)std::max<size_t>(1, want);  // one-shot: every block does one chunk
   {
     int rc = stk_grow_partials(c, (size_t)grid, s);
@@ -248,7 +249,18 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
   if (coop && grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
 
   cudaError_t err = cudaErrorNotSupported;
-  if (coop && c->k1_algo == 1) {
+  if (coop && c->k1_algo == 2 && acc_ptrs == nullptr) {
+    // multimem flavour: needs the multicast mappings of the gradient bucket and (all-reduce) of the output bucket
+    p.grad_mc = stk_mc_lookup(c, grad_ptrs[c->rank]);
+    p.out_mc = (mode == STK_REDUCE_ALL) ? stk_mc_lookup(c, out_ptrs[c->rank]) : nullptr;
+    if (p.grad_mc && (mode == STK_REDUCE_SCATTER || p.out_mc)) {
+      err = launch_reduce_nvls(c, p, grad_dtype, out_dtype, grid, s);
+      if (err != cudaSuccess && err != cudaErrorNotSupported)
+        return stk_fail(c, STK_ERR_CUDA, std::string("k_grad_reduce_nvls launch: ") + cudaGetErrorString(err));
+    }
+  }
+  if (err == cudaSuccess) return STK_OK;
+  if (coop && c->k1_algo >= 1) {
     err = launch_reduce_bulk(c, p, grad_dtype, out_dtype, grid, s);
     if (err != cudaSuccess && err != cudaErrorNotSupported)
       return stk_fail(c, STK_ERR_CUDA, std::string("k_grad_reduce_bulk launch: ") + cudaGetErrorString(err));

@@ -7,20 +7,40 @@
 // write p,m,v (12) [+ 2 for the bf16 copy] = 28 / 30.  The clip coefficient, the skip decision and the bias corrections
 // come from device memory, so there is no host synchronisation anywhere on the step.
 //
+// Gradient sources:  MAIN  -- fp32 reduced / unscaled gradients written by K1 (cross-rank routes), indexed like the state;
+//                    RAW   -- the local model-dtype bucket itself (+ optional fp32 accumulator), scaled by mul and 1/scale
+//                             here and zeroed after the read: the world == 1 route (k_grad_norm supplies norm / inf), which
+//                             drops the 6 B/element fp32 main-grad round trip.
+// Layout extras: segments (the local state is the concatenation of this rank's shard of every gradient bucket) and a range
+// table over the flat index space selecting the parameter group (per-group lr / betas / eps / weight decay ...) or skipping
+// parameters that received no gradient this step (torch skips `p.grad is None`, torch/optim/optimizer.py).
+//
 // Arithmetic follows torch/optim/adam.py (_single_tensor_adam, the path torch takes on CPU -- the oracle) and
 // torch/optim/sgd.py (_single_tensor_sgd); the clip follows torch/nn/utils/clip_grad.py:165-174 (coef = max_norm /
 // (total_norm + 1e-6), clamped to 1) and :291-292 (clamp).
-#include "ctx.cuh"
+#include <cstdlib>
+
+#include "k1_common.cuh"
 
 namespace stk {
+
+struct GroupHyperD {   // host-side doubles, converted exactly like torch converts python scalars
+  double lr, beta1, beta2, eps, weight_decay, momentum, dampening;
+  int nesterov, maximize;
+};
+struct GroupHyperS {   // what the inner loop reads (shared memory, one entry per parameter group)
+  float step_size, bc2_sqrt, b2, eps, wd, one_m_b1, one_m_b2, lr, one_m_damp, decay_mul, mom;
+  int nesterov, maximize;
+};
 
 struct OptimParams {
   float* master;
   float* m;
   float* v;
-  const float* grad;
-  size_t nvec;          // 8-float vector count
-  PtrTable lp;          // low-precision / remote parameter destinations (already offset)
+  const void* grad;     // MAIN: float*, local indexing.  RAW: model-dtype bucket, global indexing
+  const float* acc;     // RAW only
+  size_t nvec;          // 8-float vector count of the local state
+  PtrTable lp;          // low-precision / remote parameter destinations (bases; indexed globally)
   int lp_world;         // 0: none
   int lp_rank_skip;     // lp dtype == f32 and destination == master's own buffer: skip that rank (aliased)
   const stk_scaler_state_t* scaler;
@@ -28,123 +48,254 @@ struct OptimParams {
   int rank, world;
   uint32_t epoch;
   int cross_rank;       // 1: start/end block barriers around the peer stores
-  // hyper-parameters (double precision on the host side, converted exactly like torch converts python scalars)
-  double lr, beta1, beta2, eps, weight_decay, momentum, dampening;
-  int kind, nesterov, maximize, clip_kind;
+  int kind, clip_kind;
   float clip_max_norm, clip_value;
+  float grad_mul;       // RAW
+  int unscale;          // RAW: multiply by 1/loss_scale
+  int any_mom;          // SGD: some group has momentum != 0 (the buffer is written)
+  int n_groups;
+  GroupHyperD g[STK_MAX_GROUPS];
+  int n_seg;                                 // >= 1
+  uint32_t seg_local[STK_MAX_SEGMENTS + 1];  // vector units
+  uint32_t seg_global[STK_MAX_SEGMENTS];     // vector units
+  int stream_hint;                           // 1: state loads / stores carry an L2 evict_first policy (keeps the raw bucket resident)
+  int n_ranges;                              // 0: group 0 everywhere
+  const uint32_t* range_end;                 // device, ascending, vector units (global)
+  const uint8_t* range_group;                // device; bit 7: skip
 };
 
-template <int LP_DT>  // -1: none, STK_BF16, STK_F32
-__device__ __forceinline__ void store_lp(const OptimParams& p, size_t i8, const float (&x)[8]) {
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ld_f8_hint(const float* p, uint64_t pol, float (&f)[8]) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void st_f8_hint(float* p, uint64_t pol, const float (&v)[8]) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(pol)
+               : "memory");
+}
+
+// local vector index -> global vector index
+__device__ __forceinline__ size_t to_global(const OptimParams& p, size_t i) {
+  if (p.n_seg == 1) return p.seg_global[0] + (i - p.seg_local[0]);
+  int lo = 0, hi = p.n_seg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (p.seg_local[mid] <= i) lo = mid;
+    else hi = mid - 1;
+  }
+  return p.seg_global[lo] + (i - p.seg_local[lo]);
+}
+// global vector index -> range byte (group | skip bit)
+__device__ __forceinline__ unsigned range_of(const OptimParams& p, size_t gv) {
+  int lo = 0, hi = p.n_ranges - 1;
+  while (lo < hi) {  // first j with range_end[j] > gv
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&p.range_end[mid]) > gv) hi = mid;
+    else lo = mid + 1;
+  }
+  return __ldg(&p.range_group[lo]);
+}
+
+template <int LP_DT, int VPT>  // -1: none, STK_BF16, STK_F32;  VPT vectors (8 elements each), adjacent in memory
+__device__ __forceinline__ void store_lp(const OptimParams& p, size_t gv, const float (&x)[VPT][8], int nv) {
   if constexpr (LP_DT == STK_BF16) {
-    uint4 u = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    uint4 u[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+      u[k] = make_uint4(pack_bf16(x[k][0], x[k][1]), pack_bf16(x[k][2], x[k][3]), pack_bf16(x[k][4], x[k][5]),
+                        pack_bf16(x[k][6], x[k][7]));
 #pragma unroll 1
     for (int d = 0; d < p.lp_world; ++d) {
-      int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
-      st_stream16(reinterpret_cast<uint4*>(p.lp.p[dst]) + i8, u);
+      const int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
+      uint4* q = reinterpret_cast<uint4*>(p.lp.p[dst]) + gv;
+      if (VPT == 2 && nv == 2) {
+        // one 32-byte store: a full sector per posted peer write (two 16-byte halves run at half the NVLink rate)
+        asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(q), "r"(u[0].x), "r"(u[0].y),
+                     "r"(u[0].z), "r"(u[0].w), "r"(u[VPT - 1].x), "r"(u[VPT - 1].y), "r"(u[VPT - 1].z), "r"(u[VPT - 1].w)
+                     : "memory");
+      } else {
+        st_stream16(q, u[0]);
+      }
     }
   } else if constexpr (LP_DT == STK_F32) {
 #pragma unroll 1
     for (int d = 0; d < p.lp_world; ++d) {
-      int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
+      const int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
       if (dst == p.lp_rank_skip) continue;
-      st_stream_f8(reinterpret_cast<float*>(p.lp.p[dst]) + i8 * 8, x);
+#pragma unroll
+      for (int k = 0; k < VPT; ++k)
+        if (k < nv) st_stream_f8(reinterpret_cast<float*>(p.lp.p[dst]) + (gv + k) * 8, x[k]);
     }
   }
 }
 
-// PERSIST = false: one-shot launch, one 8-element vector per thread (local step; measured ~14% faster than a persistent
+// GRAD: STK_F32 with RAW = false -> MAIN.  RAW = true -> the raw bucket of dtype GRAD.
+// PERSIST = false: one-shot launch, VPT vectors per thread (local step; measured ~14% faster than a persistent
 // grid-stride loop on B200, tools/membench.cu).  PERSIST = true: co-resident grid-stride loop, required when the kernel
 // pushes its shard to peers and therefore carries the cross-rank block barriers (sharded / OSS step).
-template <int KIND, int LP_DT, bool PERSIST>
+template <int KIND, int LP_DT, bool PERSIST, int VPT, int GRAD, bool RAW>
 __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
-  __shared__ float s_bc[4];
-  __shared__ int s_skip;
-  if (PERSIST && p.cross_rank) block_barrier_all_ranks(p.pads, p.rank, p.world, 0, p.epoch);
+  __shared__ GroupHyperS s_g[STK_MAX_GROUPS];
+  __shared__ int s_skip, s_first;
+  __shared__ float s_inv_scale;
+  if (PERSIST && p.cross_rank && !block_barrier_all_ranks(p.pads, p.rank, p.world, 0, p.epoch)) return;
 
-  const float mom = (float)p.momentum;
-  const bool use_m = (KIND != STK_OPT_SGD) || mom != 0.f;
-  const size_t stride = PERSIST ? size_t(gridDim.x) * blockDim.x : 0;
-  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool use_m = (KIND != STK_OPT_SGD) || p.m != nullptr;
+  const size_t stride = PERSIST ? size_t(gridDim.x) * blockDim.x * VPT : 0;
+  size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * VPT;
 
-  // issue this thread's first loads before the (serial, double-precision) bias-correction prologue so that the pow()
-  // latency hides behind the memory latency: 4 x 32-byte loads in flight per thread (LDG.E.256)
-  f8 g, w, m, v;
-  if (i < p.nvec) {
-    g = ld_stream_f8(p.grad + i * 8);
-    w = ld_stream_f8(p.master + i * 8);
-    if (use_m) m = ld_stream_f8(p.m + i * 8);
-    if (KIND != STK_OPT_SGD) v = ld_stream_f8(p.v + i * 8);
-  }
+  float g[VPT][8], w[VPT][8], m[VPT][8], v[VPT][8];
+  const uint64_t pol = RAW ? policy_evict_first() : 0;
+  size_t gv = 0;
+  int nv = 0;
+  auto load = [&]() {
+    // issue this thread's loads before the (serial, double-precision) bias-correction prologue so that the pow()
+    // latency hides behind the memory latency: 32-byte loads (LDG.E.256), all in flight together
+    nv = (i + VPT <= p.nvec) ? VPT : (i < p.nvec ? 1 : 0);
+    if (nv == 0) return;
+    gv = to_global(p, i);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+      if (k < nv) {
+        if constexpr (RAW) InVec<GRAD>::load(p.grad, gv + k, g[k]);
+        else InVec<STK_F32>::load(p.grad, i + k, g[k]);
+        if (RAW && p.stream_hint) {
+          ld_f8_hint(p.master + (i + k) * 8, pol, w[k]);
+          if (use_m) ld_f8_hint(p.m + (i + k) * 8, pol, m[k]);
+          if (KIND != STK_OPT_SGD) ld_f8_hint(p.v + (i + k) * 8, pol, v[k]);
+        } else {
+          InVec<STK_F32>::load(p.master, i + k, w[k]);
+          if (use_m) InVec<STK_F32>::load(p.m, i + k, m[k]);
+          if (KIND != STK_OPT_SGD) InVec<STK_F32>::load(p.v, i + k, v[k]);
+        }
+      }
+    if constexpr (RAW) {
+      if (p.acc != nullptr) {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
+          if (k < nv) {
+            float a[8];
+            InVec<STK_F32>::load(p.acc, gv + k, a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[k][e] += a[e];
+          }
+      }
+    }
+  };
+  load();
+
   if (threadIdx.x == 0) {
     s_skip = p.scaler->found_inf != 0;  // GradScaler.step: no optimizer.step() at all when any grad is inf/nan
+    s_first = (p.scaler->opt_steps == 0) ? 1 : 0;  // SGD: first step seeds the momentum buffer with the gradient
+    s_inv_scale = (RAW && p.unscale) ? (float)(1.0 / (double)p.scaler->scale) : 1.f;
+  }
+  if (threadIdx.x < (unsigned)p.n_groups) {
+    const GroupHyperD& h = p.g[threadIdx.x];
+    GroupHyperS o;
     // bias corrections in double, exactly as the python scalars in torch/optim/adam.py:531-547
     const double t = (double)(p.scaler->opt_steps + 1);
+    o.step_size = 0.f;
+    o.bc2_sqrt = 1.f;
     if (KIND != STK_OPT_SGD) {
-      double bc1 = 1.0 - pow(p.beta1, t);
-      double bc2 = 1.0 - pow(p.beta2, t);
-      s_bc[0] = (float)(p.lr / bc1);  // step_size
-      s_bc[1] = (float)sqrt(bc2);     // bias_correction2_sqrt
+      const double bc1 = 1.0 - pow(h.beta1, t);
+      const double bc2 = 1.0 - pow(h.beta2, t);
+      o.step_size = (float)(h.lr / bc1);
+      o.bc2_sqrt = (float)sqrt(bc2);
     }
-    s_bc[2] = (p.scaler->opt_steps == 0) ? 1.f : 0.f;  // SGD: first step seeds the momentum buffer with the gradient
+    o.b2 = (float)h.beta2;
+    o.eps = (float)h.eps;
+    o.wd = (float)h.weight_decay;
+    o.one_m_b1 = (float)(1.0 - h.beta1);
+    o.one_m_b2 = (float)(1.0 - h.beta2);
+    o.lr = (float)h.lr;
+    o.one_m_damp = (float)(1.0 - h.dampening);
+    o.decay_mul = (float)(1.0 - h.lr * h.weight_decay);  // AdamW: param.mul_(1 - lr * wd)
+    o.mom = (float)h.momentum;
+    o.nesterov = h.nesterov;
+    o.maximize = h.maximize;
+    s_g[threadIdx.x] = o;
   }
   __syncthreads();
-  if (!s_skip) {
-    const float step_size = s_bc[0], bc2_sqrt = s_bc[1];
-    const bool first_step = s_bc[2] != 0.f;
-    float coef = 1.f;
-    if (p.clip_kind == STK_CLIP_NORM) {
-      float c = p.clip_max_norm / (p.scaler->grad_norm + 1e-6f);
-      coef = fminf(c, 1.0f);
-    }
-    const float cv = p.clip_value;
-    const float b2 = (float)p.beta2, eps = (float)p.eps, wd = (float)p.weight_decay;
-    const float one_m_b1 = (float)(1.0 - p.beta1), one_m_b2 = (float)(1.0 - p.beta2);
-    const float lr = (float)p.lr, one_m_damp = (float)(1.0 - p.dampening);
-    const float decay_mul = (float)(1.0 - p.lr * p.weight_decay);  // AdamW: param.mul_(1 - lr * wd)
+  const bool skip_all = s_skip != 0;
+  const bool first_step = s_first != 0;
+  float coef = 1.f;
+  if (p.clip_kind == STK_CLIP_NORM) coef = fminf(p.clip_max_norm / (p.scaler->grad_norm + 1e-6f), 1.0f);
+  const float cv = p.clip_value;
+  const float inv_scale = s_inv_scale;
 
-    while (i < p.nvec) {
+  while (nv > 0) {
+    unsigned rb = 0;
+    if (p.n_ranges > 0) rb = range_of(p, gv);  // the VPT vectors of a thread never straddle a parameter (16-element alignment)
+    const GroupHyperS h = s_g[rb & 0x7f];
+    const bool skip = skip_all || (rb & 0x80u);
+    if (!skip) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float gg = g.v[k];
-        if (p.clip_kind == STK_CLIP_NORM) gg *= coef;
-        else if (p.clip_kind == STK_CLIP_VALUE) gg = fminf(fmaxf(gg, -cv), cv);
-        if (p.maximize) gg = -gg;
-        float ww = w.v[k];
-        if (KIND == STK_OPT_ADAM || KIND == STK_OPT_ADAMW) {
-          if (KIND == STK_OPT_ADAMW) ww *= decay_mul;
-          else if (wd != 0.f) gg = fmaf(ww, wd, gg);          // grad.add(param, alpha=wd)
-          float mm = m.v[k];
-          mm = fmaf(one_m_b1, gg - mm, mm);                    // exp_avg.lerp_(grad, 1 - beta1)
-          float vv = v.v[k] * b2;
-          vv = fmaf(one_m_b2 * gg, gg, vv);                    // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-          float denom = sqrtf(vv) / bc2_sqrt + eps;
-          ww = ww - step_size * (mm / denom);                  // addcdiv_(exp_avg, denom, value=-step_size)
-          m.v[k] = mm; v.v[k] = vv;
-        } else {  // SGD
-          if (wd != 0.f) gg = fmaf(ww, wd, gg);
-          if (mom != 0.f) {
-            float bb = first_step ? gg : fmaf(m.v[k], mom, one_m_damp * gg);
-            m.v[k] = bb;
-            gg = p.nesterov ? fmaf(bb, mom, gg) : bb;
+      for (int k = 0; k < VPT; ++k) {
+        if (k >= nv) continue;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float gg = g[k][e];
+          if constexpr (RAW) {
+            gg *= p.grad_mul;
+            gg *= inv_scale;
           }
-          ww = fmaf(-lr, gg, ww);
+          if (p.clip_kind == STK_CLIP_NORM) gg *= coef;
+          else if (p.clip_kind == STK_CLIP_VALUE) gg = fminf(fmaxf(gg, -cv), cv);
+          if (h.maximize) gg = -gg;
+          float ww = w[k][e];
+          if (KIND == STK_OPT_ADAM || KIND == STK_OPT_ADAMW) {
+            if (KIND == STK_OPT_ADAMW) ww *= h.decay_mul;
+            else if (h.wd != 0.f) gg = fmaf(ww, h.wd, gg);          // grad.add(param, alpha=wd)
+            float mm = m[k][e];
+            mm = fmaf(h.one_m_b1, gg - mm, mm);                      // exp_avg.lerp_(grad, 1 - beta1)
+            float vv = v[k][e] * h.b2;
+            vv = fmaf(h.one_m_b2 * gg, gg, vv);                      // mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+            const float denom = sqrtf(vv) / h.bc2_sqrt + h.eps;
+            ww = ww - h.step_size * (mm / denom);                    // addcdiv_(exp_avg, denom, value=-step_size)
+            m[k][e] = mm;
+            v[k][e] = vv;
+          } else {  // SGD
+            if (h.wd != 0.f) gg = fmaf(ww, h.wd, gg);
+            if (h.mom != 0.f) {
+              const float bb = first_step ? gg : fmaf(m[k][e], h.mom, h.one_m_damp * gg);
+              m[k][e] = bb;
+              gg = h.nesterov ? fmaf(bb, h.mom, gg) : bb;
+            }
+            ww = fmaf(-h.lr, gg, ww);
+          }
+          w[k][e] = ww;
         }
-        w.v[k] = ww;
       }
-      st_stream_f8(p.master + i * 8, w.v);
-      if (use_m) st_stream_f8(p.m + i * 8, m.v);
-      if (KIND != STK_OPT_SGD) st_stream_f8(p.v + i * 8, v.v);
-      store_lp<LP_DT>(p, i, w.v);
-      if (!PERSIST) break;
-      i += stride;
-      if (i < p.nvec) {
-        g = ld_stream_f8(p.grad + i * 8);
-        w = ld_stream_f8(p.master + i * 8);
-        if (use_m) m = ld_stream_f8(p.m + i * 8);
-        if (KIND != STK_OPT_SGD) v = ld_stream_f8(p.v + i * 8);
-      }
+#pragma unroll
+      for (int k = 0; k < VPT; ++k)
+        if (k < nv) {
+          if (RAW && p.stream_hint) {
+            st_f8_hint(p.master + (i + k) * 8, pol, w[k]);
+            if (use_m && (KIND != STK_OPT_SGD || p.any_mom)) st_f8_hint(p.m + (i + k) * 8, pol, m[k]);
+            if (KIND != STK_OPT_SGD) st_f8_hint(p.v + (i + k) * 8, pol, v[k]);
+          } else {
+            st_stream_f8(p.master + (i + k) * 8, w[k]);
+            if (use_m && (KIND != STK_OPT_SGD || p.any_mom)) st_stream_f8(p.m + (i + k) * 8, m[k]);
+            if (KIND != STK_OPT_SGD) st_stream_f8(p.v + (i + k) * 8, v[k]);
+          }
+        }
+      store_lp<LP_DT, VPT>(p, gv, w, nv);
     }
+    if constexpr (RAW) {
+      // the bucket is consumed (also on a skipped step): zero it for the next backward's in-place accumulation
+#pragma unroll
+      for (int k = 0; k < VPT; ++k)
+        if (k < nv) InVec<GRAD>::zero(const_cast<void*>(p.grad), gv + k);
+    }
+    if (!PERSIST) break;
+    i += stride;
+    load();
   }
   if (PERSIST && p.cross_rank) block_barrier_all_ranks(p.pads, p.rank, p.world, 1, p.epoch);
 }
@@ -178,11 +329,15 @@ __global__ void k_step_epilogue(stk_scaler_state_t* st, StepAccum* acc) {
 
 using namespace stk;
 
+static size_t g_grid_nvec = 0;  // set under the context lock by stk_optim_step_ex (cross-rank launches only)
+
 template <typename K>
-static cudaError_t launch_one(stk_ctx* c, K kernel, const OptimParams& p, bool persist, cudaStream_t s) {
-  size_t grid = (p.nvec + 255) / 256;  // one-shot: one 8-float vector per thread
+static cudaError_t launch_one(stk_ctx* c, K kernel, const OptimParams& p, bool persist, int vpt, cudaStream_t s) {
+  const size_t per_block = size_t(256) * vpt;
+  const size_t nvec = (persist && g_grid_nvec) ? g_grid_nvec : p.nvec;  // same grid on every rank
+  size_t grid = (nvec + per_block - 1) / per_block;  // one-shot: VPT vectors per thread
   if (grid < 1) grid = 1;
-  if (persist) {  // co-resident (cooperative) grid-stride loop: at most two blocks per SM
+  if (persist) {  // co-resident grid-stride loop: at most two blocks per SM
     size_t res = (size_t)std::min(blocks_per_sm(c, kernel, 256), 2) * c->sm_count;
     if (res > (size_t)kMaxBlocks) res = kMaxBlocks;
     if (grid > res) grid = res;
@@ -192,81 +347,177 @@ static cudaError_t launch_one(stk_ctx* c, K kernel, const OptimParams& p, bool p
   cfg.blockDim = dim3(256);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = persist ? 1 : 0;
+  coop_attr(c, cfg, attr);
+  if (!persist) cfg.numAttrs = 0;
   ProfScope prof(c, 1, s);
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 template <int KIND>
-static cudaError_t launch_optim(stk_ctx* c, const OptimParams& p, int lp_dtype, cudaStream_t s) {
-  if (p.cross_rank) {
-    if (lp_dtype == STK_BF16) return launch_one(c, k_optim_step<KIND, STK_BF16, true>, p, true, s);
-    return launch_one(c, k_optim_step<KIND, STK_F32, true>, p, true, s);
+static cudaError_t launch_optim(stk_ctx* c, const OptimParams& p, int lp_dtype, int grad_dtype, bool raw, bool pair,
+                                cudaStream_t s) {
+  if (raw) {
+    // raw route: local step only (world == 1)
+    if (grad_dtype == STK_BF16 && p.lp_world == 1 && lp_dtype == STK_BF16)
+      return launch_one(c, k_optim_step<KIND, STK_BF16, false, 1, STK_BF16, true>, p, false, 1, s);
+    if (grad_dtype == STK_F32 && p.lp_world == 0)
+      return launch_one(c, k_optim_step<KIND, -1, false, 1, STK_F32, true>, p, false, 1, s);
+    return cudaErrorNotSupported;
   }
-  if (p.lp_world == 0) return launch_one(c, k_optim_step<KIND, -1, false>, p, false, s);
-  if (lp_dtype == STK_BF16) return launch_one(c, k_optim_step<KIND, STK_BF16, false>, p, false, s);
-  return launch_one(c, k_optim_step<KIND, STK_F32, false>, p, false, s);
+  if (p.cross_rank) {
+    if (lp_dtype == STK_BF16) {
+      if (pair) return launch_one(c, k_optim_step<KIND, STK_BF16, true, 2, STK_F32, false>, p, true, 2, s);
+      return launch_one(c, k_optim_step<KIND, STK_BF16, true, 1, STK_F32, false>, p, true, 1, s);
+    }
+    return launch_one(c, k_optim_step<KIND, STK_F32, true, 1, STK_F32, false>, p, true, 1, s);
+  }
+  if (p.lp_world == 0) return launch_one(c, k_optim_step<KIND, -1, false, 1, STK_F32, false>, p, false, 1, s);
+  if (lp_dtype == STK_BF16) return launch_one(c, k_optim_step<KIND, STK_BF16, false, 1, STK_F32, false>, p, false, 1, s);
+  return launch_one(c, k_optim_step<KIND, STK_F32, false, 1, STK_F32, false>, p, false, 1, s);
 }
 
 extern "C" {
 
-int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float* exp_avg, float* exp_avg_sq,
-                   const float* grad, size_t n_local, void* const* lp_ptrs, int lp_world, int lp_dtype, size_t lp_offset,
-                   void* stream) {
-  STK_REQUIRE(c, c && h && master && grad, "stk_optim_step: NULL argument");
-  STK_REQUIRE(c, n_local % 8 == 0, "stk_optim_step: n_local must be a multiple of 8");
-  STK_REQUIRE(c, h->kind >= STK_OPT_ADAM && h->kind <= STK_OPT_SGD, "stk_optim_step: bad optimizer kind");
-  STK_REQUIRE(c, h->kind == STK_OPT_SGD || (exp_avg && exp_avg_sq), "stk_optim_step: Adam needs exp_avg and exp_avg_sq");
-  STK_REQUIRE(c, !(h->kind == STK_OPT_SGD && h->momentum != 0.0 && !exp_avg), "stk_optim_step: SGD momentum needs a buffer");
-  STK_REQUIRE(c, lp_ptrs == nullptr || lp_world == 1 || lp_world == c->world, "stk_optim_step: lp_world must be 1 or world");
-  STK_REQUIRE(c, lp_ptrs == nullptr || lp_dtype == STK_BF16 || lp_dtype == STK_F32, "stk_optim_step: lp dtype");
-  if (n_local == 0 && c->world == 1) return STK_OK;
+int stk_optim_step_ex(stk_ctx* c, const stk_optim_args_t* a, void* stream) {
+  STK_REQUIRE(c, c && a && a->hyper && a->master && a->grad, "stk_optim_step_ex: NULL argument");
+  STK_REQUIRE(c, a->n_groups >= 1 && a->n_groups <= STK_MAX_GROUPS, "stk_optim_step_ex: n_groups must be in [1, 8]");
+  STK_REQUIRE(c, a->n_local % 8 == 0, "stk_optim_step_ex: n_local must be a multiple of 8");
+  const stk_optim_hyper_t* h = a->hyper;
+  STK_REQUIRE(c, h->kind >= STK_OPT_ADAM && h->kind <= STK_OPT_SGD, "stk_optim_step_ex: bad optimizer kind");
+  STK_REQUIRE(c, h->kind == STK_OPT_SGD || (a->exp_avg && a->exp_avg_sq), "stk_optim_step_ex: Adam needs exp_avg and exp_avg_sq");
+  bool any_mom = false;
+  for (int gi = 0; gi < a->n_groups; ++gi) {
+    STK_REQUIRE(c, h[gi].kind == h->kind, "stk_optim_step_ex: all groups must use the same optimizer kind");
+    any_mom |= h[gi].momentum != 0.0;
+  }
+  STK_REQUIRE(c, !(h->kind == STK_OPT_SGD && any_mom && !a->exp_avg), "stk_optim_step_ex: SGD momentum needs a buffer");
+  STK_REQUIRE(c, a->lp_ptrs == nullptr || a->lp_world == 1 || a->lp_world == c->world, "stk_optim_step_ex: lp_world must be 1 or world");
+  STK_REQUIRE(c, a->lp_ptrs == nullptr || a->lp_dtype == STK_BF16 || a->lp_dtype == STK_F32, "stk_optim_step_ex: lp dtype");
+  STK_REQUIRE(c, a->n_seg >= 0 && a->n_seg <= STK_MAX_SEGMENTS, "stk_optim_step_ex: too many segments");
+  STK_REQUIRE(c, a->n_seg == 0 || (a->seg_local && a->seg_global), "stk_optim_step_ex: segment arrays are NULL");
+  STK_REQUIRE(c, a->n_ranges == 0 || (a->range_end_vec && a->range_group), "stk_optim_step_ex: range arrays are NULL");
+  STK_REQUIRE(c, !a->grad_raw || c->world == 1 || a->lp_world <= 1, "stk_optim_step_ex: the raw gradient route is local (no peer stores)");
+  STK_REQUIRE(c, a->grad_raw || a->grad_dtype == STK_F32, "stk_optim_step_ex: reduced main gradients are fp32");
+  if (a->n_local == 0 && !(a->lp_ptrs && a->lp_world > 1)) return STK_OK;
+  const bool cross = a->lp_ptrs != nullptr && a->lp_world > 1;
+  if (cross) {
+    if (!c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_optim_step (sharded) before stk_comm_connect");
+    STK_POLL(c);
+  }
   std::lock_guard<std::mutex> lk(c->mu);
   DeviceGuard g(c->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 
   OptimParams p{};
-  p.master = master;
-  p.m = exp_avg;
-  p.v = exp_avg_sq;
-  p.grad = grad;
-  p.nvec = n_local / 8;
-  p.lp_world = lp_ptrs ? lp_world : 0;
+  p.master = a->master;
+  p.m = a->exp_avg;
+  p.v = a->exp_avg_sq;
+  p.grad = a->grad;
+  p.acc = a->grad_raw ? a->acc : nullptr;
+  p.nvec = a->n_local / 8;
+  p.lp_world = a->lp_ptrs ? a->lp_world : 0;
   p.lp_rank_skip = -1;
-  const size_t esz = lp_dtype == STK_BF16 ? 2 : 4;
+  // segments (vector units); the plain call is one segment at lp_offset
+  bool pair_ok = true;
+  if (a->n_seg == 0) {
+    STK_REQUIRE(c, a->lp_offset % 8 == 0, "stk_optim_step_ex: lp_offset must be a multiple of 8");
+    p.n_seg = 1;
+    p.seg_local[0] = 0;
+    p.seg_local[1] = (uint32_t)p.nvec;
+    p.seg_global[0] = (uint32_t)(a->lp_offset / 8);
+    pair_ok = (p.seg_global[0] % 2) == 0;
+  } else {
+    p.n_seg = a->n_seg;
+    for (int k = 0; k <= a->n_seg; ++k) {
+      STK_REQUIRE(c, a->seg_local[k] % 8 == 0, "stk_optim_step_ex: segment bounds must be multiples of 8");
+      p.seg_local[k] = (uint32_t)(a->seg_local[k] / 8);
+      if (k < a->n_seg) {
+        STK_REQUIRE(c, a->seg_global[k] % 8 == 0, "stk_optim_step_ex: segment offsets must be multiples of 8");
+        p.seg_global[k] = (uint32_t)(a->seg_global[k] / 8);
+        pair_ok &= (p.seg_local[k] % 2) == 0 && (p.seg_global[k] % 2) == 0;
+      }
+    }
+    STK_REQUIRE(c, p.seg_local[0] == 0 && p.seg_local[a->n_seg] == p.nvec, "stk_optim_step_ex: segments must tile [0, n_local)");
+  }
   for (int r = 0; r < p.lp_world; ++r) {
-    STK_REQUIRE(c, lp_ptrs[r] != nullptr, "stk_optim_step: NULL lp pointer");
-    p.lp.p[r] = static_cast<char*>(lp_ptrs[r]) + lp_offset * esz;
-    if (lp_dtype == STK_F32 && p.lp.p[r] == static_cast<void*>(master)) p.lp_rank_skip = r;
+    STK_REQUIRE(c, a->lp_ptrs[r] != nullptr, "stk_optim_step_ex: NULL lp pointer");
+    p.lp.p[r] = a->lp_ptrs[r];
+    if (a->lp_dtype == STK_F32 && p.n_seg == 1 &&
+        static_cast<char*>(a->lp_ptrs[r]) + size_t(p.seg_global[0]) * 32 == reinterpret_cast<char*>(a->master))
+      p.lp_rank_skip = r;
   }
   p.scaler = c->scaler_dev;
   p.pads = c->pads;
   p.rank = c->rank;
   p.world = c->world;
-  p.cross_rank = (p.lp_world > 1) ? 1 : 0;
-  if (p.cross_rank && !c->comm_ready) return stk_fail(c, STK_ERR_STATE, "stk_optim_step (sharded) before stk_comm_connect");
+  p.cross_rank = cross ? 1 : 0;
   p.epoch = p.cross_rank ? ++c->blk_epoch : 0;
-  p.lr = h->lr; p.beta1 = h->beta1; p.beta2 = h->beta2; p.eps = h->eps; p.weight_decay = h->weight_decay;
-  p.momentum = h->momentum; p.dampening = h->dampening;
-  p.kind = h->kind; p.nesterov = h->nesterov; p.maximize = h->maximize; p.clip_kind = h->clip_kind;
+  p.kind = h->kind;
+  p.clip_kind = h->clip_kind;
   p.clip_max_norm = (float)h->clip_max_norm;
   p.clip_value = (float)h->clip_value;
+  p.grad_mul = (float)a->grad_mul;
+  p.unscale = 0;
+  p.n_groups = a->n_groups;
+  for (int gi = 0; gi < a->n_groups; ++gi) {
+    GroupHyperD& o = p.g[gi];
+    o.lr = h[gi].lr; o.beta1 = h[gi].beta1; o.beta2 = h[gi].beta2; o.eps = h[gi].eps; o.weight_decay = h[gi].weight_decay;
+    o.momentum = h[gi].momentum; o.dampening = h[gi].dampening; o.nesterov = h[gi].nesterov; o.maximize = h[gi].maximize;
+  }
+  p.any_mom = any_mom ? 1 : 0;
+  {
+    static int hint = -1;   // STK_K2_STREAM_HINT: experiment knob (default off)
+    if (hint < 0) {
+      const char* e = std::getenv("STK_K2_STREAM_HINT");
+      hint = e ? std::atoi(e) : 0;
+    }
+    p.stream_hint = hint;
+  }
+  p.n_ranges = a->n_ranges;
+  p.range_end = a->range_end_vec;
+  p.range_group = a->range_group;
+  if (a->grad_raw) {
+    // 1/loss_scale is applied when the scaler is live; the device flag decides (enabled), so no host read
+    p.unscale = 1;
+  }
 
   cudaError_t err;
+  const bool raw = a->grad_raw != 0;
+  g_grid_nvec = cross ? (a->grid_n ? (a->grid_n + 7) / 8 : p.nvec) : 0;
   switch (h->kind) {
-    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(c, p, lp_dtype, s); break;
-    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(c, p, lp_dtype, s); break;
-    default: err = launch_optim<STK_OPT_SGD>(c, p, lp_dtype, s); break;
+    case STK_OPT_ADAM: err = launch_optim<STK_OPT_ADAM>(c, p, a->lp_dtype, a->grad_dtype, raw, pair_ok, s); break;
+    case STK_OPT_ADAMW: err = launch_optim<STK_OPT_ADAMW>(c, p, a->lp_dtype, a->grad_dtype, raw, pair_ok, s); break;
+    default: err = launch_optim<STK_OPT_SGD>(c, p, a->lp_dtype, a->grad_dtype, raw, pair_ok, s); break;
   }
+  if (err == cudaErrorNotSupported)
+    return stk_fail(c, STK_ERR_UNSUPPORTED, "stk_optim_step_ex: this gradient dtype / parameter dtype pair has no raw route");
   if (err != cudaSuccess) return stk_fail(c, STK_ERR_CUDA, std::string("k_optim_step launch: ") + cudaGetErrorString(err));
   return STK_OK;
 }
 
+int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float* exp_avg, float* exp_avg_sq,
+                   const float* grad, size_t n_local, void* const* lp_ptrs, int lp_world, int lp_dtype, size_t lp_offset,
+                   void* stream) {
+  STK_REQUIRE(c, c && h && master && grad, "stk_optim_step: NULL argument");
+  stk_optim_args_t a{};
+  a.hyper = h;
+  a.n_groups = 1;
+  a.master = master;
+  a.exp_avg = exp_avg;
+  a.exp_avg_sq = exp_avg_sq;
+  a.grad = grad;
+  a.grad_dtype = STK_F32;
+  a.n_local = n_local;
+  a.lp_ptrs = lp_ptrs;
+  a.lp_world = lp_world;
+  a.lp_dtype = lp_dtype;
+  a.lp_offset = lp_offset;
+  return stk_optim_step_ex(c, &a, stream);
+}
+
 int stk_step_epilogue(stk_ctx* c, void* stream) {
   STK_REQUIRE(c, c != nullptr, "stk_step_epilogue: NULL ctx");
+  STK_POLL(c);
   DeviceGuard g(c->device);
   k_step_epilogue<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->scaler_dev, c->accum_dev);
   STK_CUDA(c, cudaGetLastError());

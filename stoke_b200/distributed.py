@@ -26,6 +26,7 @@ class BaseDistributed:
         self._name = name
         self._verbose = verbose
         self._engine = None
+        self._state_id = None     # this runner's device state (scaler + step counters): one per Stoke object
         self._defer_sync = False
 
     def _print_info(self):
@@ -33,6 +34,18 @@ class BaseDistributed:
 
     def setup_distributed(self):
         self._engine = get_engine(device=torch.cuda.current_device(), rank=0, world=1)
+        self._state_id = self._engine.state_create()
+
+    def sync_loss_begin(self, loss):
+        """Launches the cross-rank loss mean and returns ticket(s); nothing synchronises until the value is read."""
+        if isinstance(loss, (list, tuple)):
+            return type(loss)(self._engine.loss_sync_begin(val.detach()) for val in loss)
+        return self._engine.loss_sync_begin(loss.detach())
+
+    def sync_loss_wait(self, ticket):
+        if isinstance(ticket, (list, tuple)):
+            return type(ticket)(self._engine.loss_sync_wait(t) for t in ticket)
+        return self._engine.loss_sync_wait(ticket)
 
     def wrap_distributed(self, model, grad_accum: Optional[int], optimizer=None):
         if self._verbose:
@@ -119,6 +132,13 @@ class DistributedB200DDP(BaseDistributed):
             torch.distributed.init_process_group(backend=backend.strip(), init_method=self._ddp_config.init_method)
         self._engine = get_engine(device=self._device_id, rank=torch.distributed.get_rank(),
                                   world=torch.distributed.get_world_size())
+        self._state_id = self._engine.state_create()
+        if self._ddp_config.no_sync is False:
+            import warnings
+
+            warnings.warn("Stoke -- DDPConfig.no_sync=False: the reference then all-reduces after every micro-step "
+                          "(stoke/distributed.py:666-668); this engine accumulates locally and reduces once per optimizer "
+                          "step -- the same sum with 1/grad_accum of the bytes")
 
     def wrap_distributed(self, model, grad_accum: Optional[int], optimizer=None):
         if self._verbose:

@@ -2,6 +2,7 @@
 """Optimizer-builder mixins and the data-parallel handler -- the plugin seam of
 /root/reference/stoke/extensions.py (``BaseOptimizer.build_optimizer`` :53-78, ``FairscaleOSSExtension`` :109-141,
 ``BaseDDP.handle_ddp`` :179-216, ``FairscaleSDDPExtension`` :249-286) with the engine behind it."""
+import os
 from contextlib import contextmanager
 from enum import Enum
 from typing import Dict, Optional, Type
@@ -11,7 +12,7 @@ import torch
 from . import _lib
 from .configs import ClipGradConfig, ClipGradNormConfig
 from .engine import ClipSpec
-from .optim import B200FusedOptimizer
+from .optim import B200FusedOptimizer, B200StockOptimizer, fused_supported
 
 
 def clip_spec_from_config(grad_clip) -> ClipSpec:
@@ -33,13 +34,20 @@ class BaseOptimizer:
         self._grad_clip = kwargs.get("grad_clip")
 
     def build_optimizer(self, optimizer: Type[torch.optim.Optimizer], optimizer_kwargs: Dict, model: torch.nn.Module):
+        module = model.module if isinstance(model, B200DataParallel) else model
+        fused = fused_supported(optimizer, optimizer_kwargs, module)
         if self._verbose:
             kind = "sharded (ZeRO-1) " if self._sharded_state else ""
-            self._print_device(f"Creating {kind}fused B200 optimizer: {optimizer.__name__}")
-        module = model.module if isinstance(model, B200DataParallel) else model
-        return B200FusedOptimizer(module, optimizer, optimizer_kwargs, engine=self._engine,
-                                  grad_accum=self._grad_accum, clip=clip_spec_from_config(self._grad_clip),
-                                  sharded=self._sharded_state, lp_dtype=self._lp_dtype)
+            route = "fused B200 optimizer" if fused else "stock optimizer behind the B200 gradient path"
+            self._print_device(f"Creating {kind}{route}: {optimizer.__name__}")
+        cls = B200FusedOptimizer if fused else B200StockOptimizer   # any torch.optim class works (extensions.py:53-78)
+        bucket_mb = None
+        ddp_cfg = getattr(self, "_ddp_config", None)
+        if ddp_cfg is not None and getattr(ddp_cfg, "bucket_cap_mb", None) and not os.environ.get("STK_BUCKET_MB"):
+            bucket_mb = float(ddp_cfg.bucket_cap_mb)   # DDPConfig.bucket_cap_mb (stoke/configs.py:178-188); env overrides
+        return cls(module, optimizer, optimizer_kwargs, engine=self._engine, grad_accum=self._grad_accum,
+                   clip=clip_spec_from_config(self._grad_clip), sharded=self._sharded_state, lp_dtype=self._lp_dtype,
+                   state_id=getattr(self, "_state_id", None), bucket_mb=bucket_mb)
 
 
 class FairscaleOSSExtension(BaseOptimizer):

@@ -24,20 +24,24 @@ class DeviceGradScaler:
     (state_dict keys follow torch/amp/grad_scaler.py: scale, growth_factor, backoff_factor, growth_interval,
     _growth_tracker)."""
 
-    def __init__(self, engine, init_scale=2.0**16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+    def __init__(self, engine, init_scale=2.0**16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000,
+                 state_id: int = 0):
         self._engine = engine
-        engine.scaler_set(scale=float(init_scale), growth_factor=float(growth_factor),
+        self._state = state_id   # the per-optimizer device state this scaler lives in (engine.state_create)
+        engine.scaler_set(state=state_id, scale=float(init_scale), growth_factor=float(growth_factor),
                           backoff_factor=float(backoff_factor), growth_interval=int(growth_interval), growth_tracker=0,
                           enabled=1, found_inf=0)
-        self._scale = engine.scale_tensor()
+        self._scale = engine.scale_tensor(state_id)
 
     def scale(self, outputs):
         if isinstance(outputs, (list, tuple)):
             return type(outputs)(self.scale(o) for o in outputs)
-        return outputs * self._scale.to(outputs.dtype)
+        # the scale stays fp32 (torch GradScaler does the same): an fp16 loss times 65536 must not overflow in fp16 --
+        # type promotion of two 0-dim tensors gives an fp32 product
+        return outputs * self._scale
 
     def get_scale(self) -> float:
-        return float(self._engine.scaler_get().scale)
+        return float(self._engine.scaler_get(self._state).scale)
 
     def is_enabled(self) -> bool:
         return True
@@ -51,15 +55,15 @@ class DeviceGradScaler:
 
     def update(self, new_scale=None):
         if new_scale is not None:
-            self._engine.scaler_set(scale=float(new_scale))
+            self._engine.scaler_set(state=self._state, scale=float(new_scale))
 
     def state_dict(self):
-        st = self._engine.scaler_get()
+        st = self._engine.scaler_get(self._state)
         return {"scale": st.scale, "growth_factor": st.growth_factor, "backoff_factor": st.backoff_factor,
                 "growth_interval": st.growth_interval, "_growth_tracker": st.growth_tracker}
 
     def load_state_dict(self, sd):
-        self._engine.scaler_set(scale=float(sd["scale"]), growth_factor=float(sd["growth_factor"]),
+        self._engine.scaler_set(state=self._state, scale=float(sd["scale"]), growth_factor=float(sd["growth_factor"]),
                                 backoff_factor=float(sd["backoff_factor"]), growth_interval=int(sd["growth_interval"]),
                                 growth_tracker=int(sd["_growth_tracker"]))
 
@@ -80,10 +84,8 @@ class BaseFP16:
             self._print_device(f"FP16 Mixin: Initialized scaler of type {type(self._scaler).__name__}")
 
     def wrap_fp16(self, model, optimizer=None):
-        if self._scaler is None and getattr(self, "_engine", None) is not None:
-            # no loss scaling in this mode: make sure a scaler left enabled by an earlier Stoke object in this process
-            # (the state lives in the per-process engine) does not unscale / gate this one
-            self._engine.scaler_set(enabled=0, scale=1.0, growth_tracker=0, found_inf=0)
+        # no loss scaling in this mode: this runner's own device state (engine.state_create) starts with the scaler
+        # disabled and scale 1, so nothing has to be reset here -- other Stoke objects of the process have their own state
         self._scaler_info()
         return model, optimizer
 
@@ -110,15 +112,18 @@ class BaseFP16:
 
     def backward_call(self, loss, model, optimizer):
         path = optimizer.path
-        path.ensure_grad_views()
+        sync = not getattr(self, "_defer_sync", False)
+        unscale = self._scaler is not None
         scaled = loss if self._scaler is None else self._scaler.scale(loss)
         if isinstance(scaled, (list, tuple)):
             for idx, val in enumerate(scaled):
+                # the hooks may launch per-bucket reduces only during the LAST backward of the micro-step
+                path.begin_backward(sync=sync, unscale=unscale, last=(idx == len(scaled) - 1))
                 val.backward(retain_graph=(idx == 0))
         else:
+            path.begin_backward(sync=sync, unscale=unscale)
             scaled.backward()
-        sync = not getattr(self, "_defer_sync", False)
-        path.after_backward(sync=sync, unscale=self._scaler is not None)
+        path.after_backward(sync=sync, unscale=unscale)
 
     def step_call(self, model, optimizer):
         optimizer.step()
@@ -142,7 +147,8 @@ class B200AmpFP16(BaseFP16):
     def wrap_fp16(self, model, optimizer=None):
         cfg = self._amp_config
         self._scaler = DeviceGradScaler(self._engine, init_scale=cfg.init_scale, growth_factor=cfg.growth_factor,
-                                        backoff_factor=cfg.backoff_factor, growth_interval=cfg.growth_interval)
+                                        backoff_factor=cfg.backoff_factor, growth_interval=cfg.growth_interval,
+                                        state_id=self._state_id)
         self._scaler_info()
         return model, optimizer
 

@@ -136,31 +136,66 @@ class Stoke:
 
     def loss(self, *args, **kwargs):
         with self._runner.loss_context:
-            if isinstance(self._loss, (list, tuple)):
-                loss = type(self._loss)(fn(*args, **kwargs) for fn in self._loss)
-                synced = [self.detach_and_sync_loss(val) for val in loss]
-                self._last_step_loss = type(self._loss)(synced)
-                self._agg_loss = type(self._loss)(a + s for a, s in zip(self._agg_loss, synced))
-                self._handle_ema_loss(loss=synced)
-                if self.grad_accum > 1 and self.model_access.training:
-                    loss = type(loss)(val / self.grad_accum for val in loss)
+            multi = isinstance(self._loss, (list, tuple))
+            loss = type(self._loss)(fn(*args, **kwargs) for fn in self._loss) if multi else self._loss(*args, **kwargs)
+            # The cross-rank mean is launched here and READ LATER: the value lands in a pinned ring and is folded into
+            # step_loss / the accumulated loss / the EMA when one of them is looked at (reference: item() + barrier() +
+            # all_reduce() + item() per micro-step, stoke/distributed.py:619-646).  No host synchronisation in the loop.
+            begin = getattr(self._runner, "sync_loss_begin", None)
+            if begin is not None:
+                self._loss_queue.append(("loss", begin(loss)))
+                if len(self._loss_queue) >= 128:   # far below the ring size; old entries completed long ago
+                    self._fold_losses()
+            elif multi:
+                self._fold_one([self.detach_and_sync_loss(val) for val in loss])
             else:
-                loss = self._loss(*args, **kwargs)
-                synced = self.detach_and_sync_loss(loss)
-                self._last_step_loss = synced
-                self._agg_loss += synced
-                self._handle_ema_loss(loss=synced)
-                if self.grad_accum > 1 and self.model_access.training:
-                    loss = loss / self.grad_accum
+                self._fold_one(self.detach_and_sync_loss(loss))
+            if self.grad_accum > 1 and self.model_access.training:
+                loss = type(loss)(val / self.grad_accum for val in loss) if multi else loss / self.grad_accum
             return loss
+
+    def _fold_one(self, synced):
+        if isinstance(self._loss, (list, tuple)):
+            synced = type(self._loss)(synced)
+            self._last = synced
+            self._agg = type(self._loss)(a + s for a, s in zip(self._agg, synced))
+        else:
+            self._last = synced
+            self._agg += synced
+        self._handle_ema_loss(loss=synced)
+
+    def _fold_losses(self):
+        """Materialises the queued loss means in order (the only place the training loop can wait on the device)."""
+        queue, self._loss_queue = self._loss_queue, []
+        for kind, ticket in queue:
+            if kind == "reset":
+                self._agg = self._set_loss_to_zero()
+            else:
+                self._fold_one(self._runner.sync_loss_wait(ticket))
+
+    def _lazy(name):  # noqa: N805 -- the three tracked values fold the queue before they are read
+        def get(self):
+            if self._loss_queue:
+                self._fold_losses()
+            return getattr(self, name)
+
+        def put(self, value):
+            if getattr(self, "_loss_queue", None):
+                self._fold_losses()
+            setattr(self, name, value)
+        return property(get, put)
+
+    _last_step_loss = _lazy("_last")
+    _agg_loss = _lazy("_agg")
+    _rolling_mean_loss = _lazy("_ema")
+    del _lazy
 
     def _handle_ema_loss(self, loss):
         self._rolling_loss_steps += 1
         if isinstance(loss, (list, tuple)):
-            self._rolling_mean_loss = type(self._rolling_mean_loss)(
-                self._ema_loss(value=val, current_mean=self._rolling_mean_loss[idx]) for idx, val in enumerate(loss))
+            self._ema = type(self._ema)(self._ema_loss(value=val, current_mean=self._ema[idx]) for idx, val in enumerate(loss))
         else:
-            self._rolling_mean_loss = self._ema_loss(value=loss, current_mean=self._rolling_mean_loss)
+            self._ema = self._ema_loss(value=loss, current_mean=self._ema)
 
     def _ema_loss(self, value: float, current_mean: float) -> float:
         if self._rolling_loss_steps == 1:
@@ -193,7 +228,10 @@ class Stoke:
             self.print("Resetting all grad/variables for next optimizer step")
         self.zero_grads()
         self._grad_accum_counter = 0
-        self._agg_loss = self._set_loss_to_zero()
+        if self._loss_queue:
+            self._loss_queue.append(("reset", None))   # keeps its place in the order of the queued loss means
+        else:
+            self._agg = self._set_loss_to_zero()
 
     # ---- helpers with the reference's names ----------------------------------------------------------------------------
     def print(self, msg, single_line: bool = False):
@@ -284,13 +322,25 @@ class Stoke:
         self._grad_accum_counter = 0
         self._optimizer_steps = 0
         self._backward_steps = 0
-        self._last_step_loss = self._set_loss_to_zero()
-        self._agg_loss = self._set_loss_to_zero()
-        self._rolling_mean_loss = self._set_loss_to_zero()
+        self._loss_queue = []
+        self._last = self._set_loss_to_zero()
+        self._agg = self._set_loss_to_zero()
+        self._ema = self._set_loss_to_zero()
         self._rolling_loss_steps = 0
 
     def barrier(self):
         self._runner.barrier()
+
+    def close(self):
+        """Releases the engine's flat buffers (peer mappings, multicast bindings, per-optimizer device state) and hands the
+        model its parameters back in ordinary torch storage.  Under DDP call it on every rank at the same point."""
+        if self._loss_queue:
+            self._fold_losses()
+        opt = getattr(self, "_optimizer", None)
+        if opt is not None and hasattr(opt, "close"):
+            if self.is_ddp:
+                self._runner.barrier()
+            opt.close()
 
     # ---- properties ----------------------------------------------------------------------------------------------------
     @property

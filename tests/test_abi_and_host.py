@@ -151,3 +151,18 @@ def test_replicas_are_disjoint_and_cover(lib):
     assert len({len(l) for l in lists}) == 1
     counts = np.bincount(np.concatenate(lists), minlength=n)
     assert counts.min() >= 1
+
+
+def test_descriptor_passing_between_processes(tmp_path):
+    """The VMM back end hands cuMemExportToShareableHandle descriptors to the peer ranks over an abstract unix socket
+    (stoke_b200/csrc/fdpass.h, SCM_RIGHTS).  Pure POSIX: compiled with g++ and run between two processes here."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "test_fdpass"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", os.path.join(root, "tools", "test_fdpass.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "fdpass ok" in out.stdout, out.stdout + out.stderr

@@ -17,33 +17,36 @@ def _run(world, tmp_path, port, algo="ldg"):
     out = tmp_path / f"mgpu_{world}_{algo}.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), str(out)]
-    env = dict(os.environ, STK_K1_ALGO=algo)  # cross-rank K1 flavour: register-staged loads | bulk-async through smem
+    # cross-rank K1 flavour: register-staged loads | bulk-async through smem | multimem (NVLS); tiny gradient buckets in the
+    # Stoke-API section so that the per-bucket launches from autograd hooks are exercised on a small model
+    env = dict(os.environ, STK_K1_ALGO=algo, STK_BUCKET_MB="0.0005")
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-4000:]
     with open(out) as f:
         return json.load(f)
 
 
-@pytest.mark.parametrize("algo", ["ldg", "bulk"])
+@pytest.mark.parametrize("algo", ["ldg", "bulk", "nvls"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_parity(world, algo, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    res = _run(world, tmp_path, 29500 + world + (10 if algo == "bulk" else 0), algo)
+    res = _run(world, tmp_path, 29500 + world + {"ldg": 0, "bulk": 10, "nvls": 20}[algo], algo)
     for name, r in res.items():
         if not isinstance(r, dict) or "rel_err" not in r:
             continue
-        assert r["rel_err"] < 1e-5, (name, r)
+        assert r["rel_err"] < r["tol"], (name, r)
         assert r["replicas_identical"], (name, r)
         assert r["model_is_rounded_master"], (name, r)
         if r["norm_rel_err"] is not None:
-            assert r["norm_rel_err"] < 1e-5, (name, r)
+            assert r["norm_rel_err"] < max(1e-5, 0.1 * r["tol"]), (name, r)
     assert res["loss_sync"] == res["loss_sync_expected"]
-    kat = res["kat_full_size"]
-    assert kat["exact"] and kat["bucket_zeroed"] and kat["norm_rel_err"] < 1e-6, kat
+    for key in ("kat_full_size", "kat_full_size_sharded"):
+        kat = res[key]
+        assert kat["exact"] and kat["bucket_zeroed"] and kat["norm_rel_err"] < 1e-6, (key, kat)
     for name, r in res["stoke_api"].items():
         assert r["replicas_identical"] and r["buffers_identical"] and r["loss_identical_across_ranks"], (name, r)
         assert r["resume_bit_identical"], (name, r)
-        assert r["opt_steps"] == 6 and r["sharded"] == (name != "ddp"), (name, r)
+        assert r["opt_steps"] == 6 and r["sharded"] and r["buckets"] > 1 and r["overlap"], (name, r)
     inf = res["inf_skip"]
     assert inf["unchanged"] and inf["scale"] == 128.0 and inf["skipped"] == 1 and inf["steps"] == 0
