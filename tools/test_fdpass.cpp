@@ -30,11 +30,11 @@ int main() {
     _exit(0);
   }
   stk_fd::FdServer srv;
-  if (!srv.start(7)) return 3;
   {
     std::lock_guard<std::mutex> lk(srv.mu);
-    srv.exported.insert(pipefd[0]);
+    srv.exported.insert(pipefd[0]);  // exported before anybody can ask for it (vmm.cu: before the blob is handed out)
   }
+  if (!srv.start(7)) return 3;
   if (write(pipefd[1], "hello", 5) != 5) return 4;
   int status = 0;
   waitpid(child, &status, 0);
