@@ -168,10 +168,11 @@ def parity_check(eng, rank, world):
     res, ok = {}, True
 
     class Big(torch.nn.Module):
-        def __init__(self, n):
+        def __init__(self, n, pieces=7):
             super().__init__()
-            self.a = torch.nn.Parameter(torch.zeros(n - n // 3))
-            self.b = torch.nn.Parameter(torch.zeros(n // 3))
+            sizes = [n // pieces] * (pieces - 1)
+            sizes.append(n - sum(sizes))
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(k)) for k in sizes])
 
     def all_true(flag: bool) -> bool:
         t = torch.tensor([1.0 if flag else 0.0], device=dev)
@@ -312,6 +313,13 @@ def build_workload(args, sb, torch, local_rank, world, rank):
         mask = torch.from_numpy((np.arange(L)[None, :] < ll[:, None]).astype(np.int64)).pin_memory()
         y = torch.from_numpy(rng.integers(0, 2, size=(batch,))).pin_memory()
         pool.append((ids, mask, y))
+    pool.sort(key=lambda b: b[0].shape[1])
+    # one batch per distinct padded length first, so that a short warm-up visits every shape
+    firsts, rest, seen = [], [], set()
+    for b in pool:
+        (firsts if b[0].shape[1] not in seen else rest).append(b)
+        seen.add(b[0].shape[1])
+    pool = firsts + rest
     resident = [tuple(t.to(dev) for t in b) for b in pool]
     counter = {"i": 0}
 
@@ -336,7 +344,7 @@ def build_workload(args, sb, torch, local_rank, world, rank):
         return s.step_loss
 
     h2d = int(sum(sum(t.numel() * t.element_size() for t in b) for b in pool) / len(pool))
-    extras = {"sampler_setup_ms": sampler_ms, "dataset_items": n_items, "buckets": 16,
+    extras = {"_distinct_shapes": len(seen), "sampler_setup_ms": sampler_ms, "dataset_items": n_items, "buckets": 16,
               "mean_padded_len": float(sum(b[0].shape[1] for b in pool) / len(pool))}
     return s, step_resident, step_e2e, batch, h2d, "bert_base_synthetic_bucketed_sampler_ddp_bf16_adamw_clipnorm1.0", extras
 
@@ -408,6 +416,8 @@ def main():
         return float(ms.item())
 
     warm = max(3, args.warmup)
+    if args.workload == "bert":
+        warm = max(warm, extras.pop("_distinct_shapes", 0) + 2)   # every padded length once: cuBLASLt / SDPA plans are per shape
     for _ in range(warm):
         step_resident()
     if args.ncu_step:

@@ -35,6 +35,8 @@ struct NormParams {
   float mul, norm_p;
   int norm_kind;
   uint32_t flags;
+  int keep_l2;       // 1 (default; STK_NORM_L2_KEEP=0 disables): loads carry an L2 evict_last policy -- the fused step's second
+                     // read of a bucket that fits L2 then hits: measured -4 us on K2 at ResNet-50 size (profiles/kernels_r02.md)
   stk_scaler_state_t* scaler;
   StepAccum* accum;
   float* blk_partial;
@@ -45,9 +47,10 @@ struct RawVec;  // the raw words of one 8-element vector (kept packed until use:
 template <>
 struct RawVec<STK_F32> {
   uint4 a, b;
-  __device__ void load(const void* base, size_t v, uint64_t pol) {
-    a = ld16_keep(reinterpret_cast<const uint4*>(base) + 2 * v, pol);
-    b = ld16_keep(reinterpret_cast<const uint4*>(base) + 2 * v + 1, pol);
+  __device__ void load(const void* base, size_t v, uint64_t pol, bool keep) {
+    const uint4* q = reinterpret_cast<const uint4*>(base) + 2 * v;
+    a = keep ? ld16_keep(q, pol) : ld_stream16(q);
+    b = keep ? ld16_keep(q + 1, pol) : ld_stream16(q + 1);
   }
   __device__ void unpack(float (&f)[8]) const {
     f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
@@ -57,7 +60,10 @@ struct RawVec<STK_F32> {
 template <int DT16>
 struct RawVec16 {
   uint4 u;
-  __device__ void load(const void* base, size_t v, uint64_t pol) { u = ld16_keep(reinterpret_cast<const uint4*>(base) + v, pol); }
+  __device__ void load(const void* base, size_t v, uint64_t pol, bool keep) {
+    const uint4* q = reinterpret_cast<const uint4*>(base) + v;
+    u = keep ? ld16_keep(q, pol) : ld_stream16(q);
+  }
   __device__ void unpack(float (&f)[8]) const {
     const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -75,49 +81,46 @@ struct RawVec<STK_F16> : RawVec16<STK_F16> {};
 constexpr int kNormThreads = 256;
 constexpr int kNormUnroll = 8;  // 8 independent 16-byte loads per thread: 32 KB in flight per block
 
+// One-shot blocks (one tile of kNormThreads * kNormUnroll vectors each, the shape that streams best on this part,
+// tools/membench.cu): load, reduce, write ONE partial, retire -- no ticket, no fence, no block waits on an atomic.  The
+// partials are folded by k_grad_norm_finish, a single block launched right behind on the same stream (stream order is the
+// only synchronisation), in a fixed order -> run-to-run deterministic.
 template <int IN_DT, bool HAS_ACC>
 __global__ void __launch_bounds__(kNormThreads) k_grad_norm(const NormParams p) {
   __shared__ float s_red[32];
-  __shared__ unsigned s_last;
   const uint64_t pol = policy_evict_last();
   float inv_scale = 1.f;
   if (p.flags & STK_RF_UNSCALE) inv_scale = (float)(1.0 / (double)p.scaler->scale);
   const float mul = p.mul;
   float part = 0.f;
   bool bad = false;
-  // one balanced wave: every block owns one contiguous chunk of ceil(nvec / grid) vectors (no tile hand-out, no ragged last
-  // wave), swept kNormUnroll independent 16-byte loads per thread at a time
-  const size_t chunk = (p.nvec + gridDim.x - 1) / gridDim.x;
-  const size_t cbeg = size_t(blockIdx.x) * chunk;
-  const size_t cend = cbeg + chunk < p.nvec ? cbeg + chunk : p.nvec;
-  for (size_t t0 = cbeg; t0 < cend; t0 += size_t(kNormThreads) * kNormUnroll) {
-    RawVec<IN_DT> raw[kNormUnroll];
+  const size_t t0 = size_t(blockIdx.x) * kNormThreads * kNormUnroll;
+  RawVec<IN_DT> raw[kNormUnroll];
 #pragma unroll
-    for (int u = 0; u < kNormUnroll; ++u) {
-      const size_t v = t0 + size_t(u) * kNormThreads + threadIdx.x;
-      if (v < cend) raw[u].load(p.grad, v, pol);
-    }
+  for (int u = 0; u < kNormUnroll; ++u) {
+    const size_t v = t0 + size_t(u) * kNormThreads + threadIdx.x;
+    if (v < p.nvec) raw[u].load(p.grad, v, pol, p.keep_l2 != 0);
+  }
 #pragma unroll
-    for (int u = 0; u < kNormUnroll; ++u) {
-      const size_t v = t0 + size_t(u) * kNormThreads + threadIdx.x;
-      if (v < cend) {
-        float g[8];
-        raw[u].unpack(g);
-        if (HAS_ACC) {
-          float a[8];
-          InVec<STK_F32>::load(p.acc, v, a);
+  for (int u = 0; u < kNormUnroll; ++u) {
+    const size_t v = t0 + size_t(u) * kNormThreads + threadIdx.x;
+    if (v < p.nvec) {
+      float g[8];
+      raw[u].unpack(g);
+      if (HAS_ACC) {
+        float a[8];
+        InVec<STK_F32>::load(p.acc, v, a);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] += a[i];
-        }
+        for (int i = 0; i < 8; ++i) g[i] += a[i];
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x = g[i] * mul;
-          bad |= !finitef(x);
-          x *= inv_scale;
-          if (p.norm_kind == STK_NORM_L2) part = fmaf(x, x, part);
-          else if (p.norm_kind == STK_NORM_INF) part = fmaxf(part, fabsf(x));
-          else if (p.norm_kind == STK_NORM_P) part += __powf(fabsf(x), p.norm_p);
-        }
+      for (int i = 0; i < 8; ++i) {
+        float x = g[i] * mul;
+        bad |= !finitef(x);
+        x *= inv_scale;
+        if (p.norm_kind == STK_NORM_L2) part = fmaf(x, x, part);
+        else if (p.norm_kind == STK_NORM_INF) part = fmaxf(part, fabsf(x));
+        else if (p.norm_kind == STK_NORM_P) part += __powf(fabsf(x), p.norm_p);
       }
     }
   }
@@ -125,30 +128,35 @@ __global__ void __launch_bounds__(kNormThreads) k_grad_norm(const NormParams p) 
   const float blk = mx ? block_reduce<true>(part, s_red) : block_reduce<false>(part, s_red);
   const int any_bad = __syncthreads_or(bad ? 1 : 0);
   if (threadIdx.x == 0) {
-    p.blk_partial[blockIdx.x] = blk;
-    if (any_bad) atomicOr(&p.accum->found_inf, 1u);
-    __threadfence();
-    s_last = (atomicAdd(&p.accum->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    // sign bit of the partial carries the block's inf/nan verdict (partials are >= 0 for every norm kind)
+    p.blk_partial[blockIdx.x] = any_bad ? -1.f - fminf(blk, 3.0e38f) : blk;
   }
-  __syncthreads();
-  if (!s_last) return;
-  // last block: fold the (at most a few hundred) block partials in a fixed order -> run-to-run deterministic
-  __threadfence();
+}
+
+__global__ void __launch_bounds__(1024) k_grad_norm_finish(const NormParams p, unsigned nblocks) {
+  __shared__ float s_red[32];
+  const bool mx = p.norm_kind == STK_NORM_INF;
   float x = 0.f;
-  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-    const float y = __ldcg(&p.blk_partial[b]);
+  bool bad = false;
+  for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    float y = __ldcg(&p.blk_partial[b]);
+    if (y < 0.f) {
+      bad = true;
+      y = -1.f - y;
+    }
     x = mx ? fmaxf(x, y) : x + y;
   }
   const float tot = mx ? block_reduce<true>(x, s_red) : block_reduce<false>(x, s_red);
+  const int any_bad = __syncthreads_or(bad ? 1 : 0);
   if (threadIdx.x == 0) {
     float run = p.accum->norm_partial;
     run = mx ? fmaxf(run, tot) : run + tot;
-    uint32_t inf = atomicOr(&p.accum->found_inf, 0u);
-    p.accum->blocks_done = 0;
+    uint32_t inf = p.accum->found_inf | (any_bad ? 1u : 0u);
     if (p.flags & STK_RF_FINAL) {
       float norm = run;
       if (p.norm_kind == STK_NORM_L2) norm = sqrtf(run);
       else if (p.norm_kind == STK_NORM_P) norm = powf(run, 1.f / p.norm_p);
+      if (inf) norm = __int_as_float(0x7f800000);  // an inf/nan gradient: torch's total_norm is inf (or nan) too
       p.scaler->grad_norm = norm;
       // the inf gate belongs to the loss scaler (GradScaler.step); without one the reference steps regardless
       p.scaler->found_inf = (inf && (p.flags & STK_RF_UNSCALE)) ? 1 : 0;
@@ -197,20 +205,21 @@ int stk_grad_norm(stk_ctx* c, const void* grad, int grad_dtype, const float* acc
   p.norm_p = (float)norm_p;
   p.norm_kind = norm_kind;
   p.flags = flags;
+  {
+    static int keep = -1;
+    if (keep < 0) {
+      const char* e = std::getenv("STK_NORM_L2_KEEP");
+      keep = e ? std::atoi(e) : 1;
+    }
+    p.keep_l2 = keep;
+  }
   p.scaler = c->scaler_dev;
   p.accum = c->accum_dev;
   const size_t tile = size_t(kNormThreads) * kNormUnroll;
   size_t want = (p.nvec + tile - 1) / tile;
   if (want < 1) want = 1;
-  static int per_sm_cap = -1;   // STK_NORM_BLOCKS_PER_SM: tuning knob (default: the kernel's occupancy)
-  if (per_sm_cap < 0) {
-    const char* e = std::getenv("STK_NORM_BLOCKS_PER_SM");
-    per_sm_cap = e ? std::atoi(e) : 0;
-  }
-  // persistent grid: every SM filled to the kernel's occupancy
   void (*kern)(NormParams) = nullptr;
-#define STK_PICK(DT)                                            \
-  kern = acc ? k_grad_norm<DT, true> : k_grad_norm<DT, false>;
+#define STK_PICK(DT) kern = acc ? k_grad_norm<DT, true> : k_grad_norm<DT, false>;
   switch (grad_dtype) {
     case STK_F32: STK_PICK(STK_F32) break;
     case STK_BF16: STK_PICK(STK_BF16) break;
@@ -218,15 +227,13 @@ int stk_grad_norm(stk_ctx* c, const void* grad, int grad_dtype, const float* acc
     default: return stk_fail(c, STK_ERR_INVALID, "stk_grad_norm: bad dtype");
   }
 #undef STK_PICK
-  int per_sm = blocks_per_sm(c, kern, kNormThreads);
-  if (per_sm_cap > 0 && per_sm_cap < per_sm) per_sm = per_sm_cap;
-  const size_t resident = (size_t)per_sm * c->sm_count;
-  const unsigned grid = (unsigned)std::min(want, resident);
+  const unsigned grid = (unsigned)want;
   int rc = stk_grow_partials(c, grid, s);
   if (rc != STK_OK) return rc;
   p.blk_partial = c->blk_partial_dev;
   ProfScope prof(c, 3, s);
   kern<<<grid, kNormThreads, 0, s>>>(p);
+  k_grad_norm_finish<<<1, 1024, 0, s>>>(p, grid);
   STK_CUDA(c, cudaGetLastError());
   return STK_OK;
 }

@@ -35,7 +35,11 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) k_grad_reduce_nvls(const Redu
   const bool all = p.n_dst > 1;
 
   const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t v0 = p.vec_begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x; v0 < p.vec_end; v0 += stride * U) {
+  const unsigned lane = threadIdx.x & 31;
+  // the loop variable is warp-uniform (all lanes of a warp iterate together: the fp32 publish below shuffles between lanes);
+  // a lane past the end of the shard is merely inactive
+  for (size_t w0 = p.vec_begin + size_t(blockIdx.x) * blockDim.x + (threadIdx.x - lane); w0 < p.vec_end; w0 += stride * U) {
+    const size_t v0 = w0 + lane;
     float x[U][8];
     // every multimem load of this round is issued before the first use (one switch round trip per round)
 #pragma unroll
@@ -56,12 +60,16 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) k_grad_reduce_nvls(const Redu
             x[u][2 * j + 1] = (IN_DT == STK_BF16) ? bf16hi(w4[j]) : f16hi(w4[j]);
           }
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[u][i] = 0.f;
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t v = v0 + u * stride;
-      if (v < p.vec_end) {
+      const bool active = v < p.vec_end;
+      if (active) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float y = x[u][i] * mul;
@@ -72,21 +80,43 @@ __global__ void __launch_bounds__(kNvlsThreads, 1) k_grad_reduce_nvls(const Redu
           else if (p.norm_kind == STK_NORM_INF) part = fmaxf(part, fabsf(y));
           else if (p.norm_kind == STK_NORM_P) part += __powf(fabsf(y), p.norm_p);
         }
-        if (all) {
-          if constexpr (OUT_DT == STK_F32) {
-            char* dst = reinterpret_cast<char*>(p.out_mc) + v * 32;
-            mm_st16(dst, make_uint4(__float_as_uint(x[u][0]), __float_as_uint(x[u][1]), __float_as_uint(x[u][2]),
-                                    __float_as_uint(x[u][3])));
-            mm_st16(dst + 16, make_uint4(__float_as_uint(x[u][4]), __float_as_uint(x[u][5]), __float_as_uint(x[u][6]),
-                                         __float_as_uint(x[u][7])));
-          } else {
-            mm_st16(reinterpret_cast<char*>(p.out_mc) + v * 16,
-                    make_uint4(pack_bf16(x[u][0], x[u][1]), pack_bf16(x[u][2], x[u][3]), pack_bf16(x[u][4], x[u][5]),
-                               pack_bf16(x[u][6], x[u][7])));
+      }
+      if (all) {  // uniform
+        if constexpr (OUT_DT == STK_F32) {
+          // multimem.st moves at most 16 bytes per thread; two 16-byte stores per thread at a 32-byte thread stride would
+          // write half sectors (measured with plain peer stores: half the NVLink rate).  Lane pairs swap halves instead, so
+          // that each store instruction covers whole 32-byte sectors: the even lane's vector, then the odd lane's.
+          // (shards start on even vector indices -- stk_shard_range -- so lane parity == vector parity)
+          const bool odd = lane & 1;
+          float take[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) take[i] = __shfl_xor_sync(0xffffffffu, odd ? x[u][i] : x[u][4 + i], 1);
+          const bool pair_ok = active && ((v ^ 1) < p.vec_end);
+          if (pair_ok) {
+            // ONE store instruction per sector row for both lanes of the pair (select data and address, do not branch)
+            char* even_vec = reinterpret_cast<char*>(p.out_mc) + (v & ~size_t(1)) * 32 + (odd ? 16 : 0);
+            float d1[4], d2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              d1[i] = odd ? take[i] : x[u][i];        // row of the even vector: [even lane: its 0..3 | odd lane: even's 4..7]
+              d2[i] = odd ? x[u][4 + i] : take[i];    // row of the odd vector:  [even lane: odd's 0..3 | odd lane: its 4..7]
+            }
+            mm_st16(even_vec, make_uint4(__float_as_uint(d1[0]), __float_as_uint(d1[1]), __float_as_uint(d1[2]), __float_as_uint(d1[3])));
+            mm_st16(even_vec + 32, make_uint4(__float_as_uint(d2[0]), __float_as_uint(d2[1]), __float_as_uint(d2[2]), __float_as_uint(d2[3])));
+          } else if (active) {
+            char* mine = reinterpret_cast<char*>(p.out_mc) + v * 32;
+            mm_st16(mine, make_uint4(__float_as_uint(x[u][0]), __float_as_uint(x[u][1]), __float_as_uint(x[u][2]),
+                                     __float_as_uint(x[u][3])));
+            mm_st16(mine + 16, make_uint4(__float_as_uint(x[u][4]), __float_as_uint(x[u][5]), __float_as_uint(x[u][6]),
+                                          __float_as_uint(x[u][7])));
           }
-        } else {
-          store_out<OUT_DT>(p.out.p[p.rank], v, x[u]);
+        } else if (active) {
+          mm_st16(reinterpret_cast<char*>(p.out_mc) + v * 16,
+                  make_uint4(pack_bf16(x[u][0], x[u][1]), pack_bf16(x[u][2], x[u][3]), pack_bf16(x[u][4], x[u][5]),
+                             pack_bf16(x[u][6], x[u][7])));
         }
+      } else if (active) {
+        store_out<OUT_DT>(p.out.p[p.rank], v, x[u]);
       }
     }
   }

@@ -18,8 +18,6 @@
 // Arithmetic follows torch/optim/adam.py (_single_tensor_adam, the path torch takes on CPU -- the oracle) and
 // torch/optim/sgd.py (_single_tensor_sgd); the clip follows torch/nn/utils/clip_grad.py:165-174 (coef = max_norm /
 // (total_norm + 1e-6), clamped to 1) and :291-292 (clamp).
-#include <cstdlib>
-
 #include "k1_common.cuh"
 
 namespace stk {
@@ -58,27 +56,10 @@ struct OptimParams {
   int n_seg;                                 // >= 1
   uint32_t seg_local[STK_MAX_SEGMENTS + 1];  // vector units
   uint32_t seg_global[STK_MAX_SEGMENTS];     // vector units
-  int stream_hint;                           // 1: state loads / stores carry an L2 evict_first policy (keeps the raw bucket resident)
   int n_ranges;                              // 0: group 0 everywhere
   const uint32_t* range_end;                 // device, ascending, vector units (global)
   const uint8_t* range_group;                // device; bit 7: skip
 };
-
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void ld_f8_hint(const float* p, uint64_t pol, float (&f)[8]) {
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
-               : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void st_f8_hint(float* p, uint64_t pol, const float (&v)[8]) {
-  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "f"(v[0]),
-               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(pol)
-               : "memory");
-}
 
 // local vector index -> global vector index
 __device__ __forceinline__ size_t to_global(const OptimParams& p, size_t i) {
@@ -151,7 +132,6 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
   size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * VPT;
 
   float g[VPT][8], w[VPT][8], m[VPT][8], v[VPT][8];
-  const uint64_t pol = RAW ? policy_evict_first() : 0;
   size_t gv = 0;
   int nv = 0;
   auto load = [&]() {
@@ -165,15 +145,9 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
       if (k < nv) {
         if constexpr (RAW) InVec<GRAD>::load(p.grad, gv + k, g[k]);
         else InVec<STK_F32>::load(p.grad, i + k, g[k]);
-        if (RAW && p.stream_hint) {
-          ld_f8_hint(p.master + (i + k) * 8, pol, w[k]);
-          if (use_m) ld_f8_hint(p.m + (i + k) * 8, pol, m[k]);
-          if (KIND != STK_OPT_SGD) ld_f8_hint(p.v + (i + k) * 8, pol, v[k]);
-        } else {
-          InVec<STK_F32>::load(p.master, i + k, w[k]);
-          if (use_m) InVec<STK_F32>::load(p.m, i + k, m[k]);
-          if (KIND != STK_OPT_SGD) InVec<STK_F32>::load(p.v, i + k, v[k]);
-        }
+        InVec<STK_F32>::load(p.master, i + k, w[k]);
+        if (use_m) InVec<STK_F32>::load(p.m, i + k, m[k]);
+        if (KIND != STK_OPT_SGD) InVec<STK_F32>::load(p.v, i + k, v[k]);
       }
     if constexpr (RAW) {
       if (p.acc != nullptr) {
@@ -275,15 +249,9 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
 #pragma unroll
       for (int k = 0; k < VPT; ++k)
         if (k < nv) {
-          if (RAW && p.stream_hint) {
-            st_f8_hint(p.master + (i + k) * 8, pol, w[k]);
-            if (use_m && (KIND != STK_OPT_SGD || p.any_mom)) st_f8_hint(p.m + (i + k) * 8, pol, m[k]);
-            if (KIND != STK_OPT_SGD) st_f8_hint(p.v + (i + k) * 8, pol, v[k]);
-          } else {
-            st_stream_f8(p.master + (i + k) * 8, w[k]);
-            if (use_m && (KIND != STK_OPT_SGD || p.any_mom)) st_stream_f8(p.m + (i + k) * 8, m[k]);
-            if (KIND != STK_OPT_SGD) st_stream_f8(p.v + (i + k) * 8, v[k]);
-          }
+          st_stream_f8(p.master + (i + k) * 8, w[k]);
+          if (use_m && (KIND != STK_OPT_SGD || p.any_mom)) st_stream_f8(p.m + (i + k) * 8, m[k]);
+          if (KIND != STK_OPT_SGD) st_stream_f8(p.v + (i + k) * 8, v[k]);
         }
       store_lp<LP_DT, VPT>(p, gv, w, nv);
     }
@@ -465,14 +433,6 @@ int stk_optim_step_ex(stk_ctx* c, const stk_optim_args_t* a, void* stream) {
     o.momentum = h[gi].momentum; o.dampening = h[gi].dampening; o.nesterov = h[gi].nesterov; o.maximize = h[gi].maximize;
   }
   p.any_mom = any_mom ? 1 : 0;
-  {
-    static int hint = -1;   // STK_K2_STREAM_HINT: experiment knob (default off)
-    if (hint < 0) {
-      const char* e = std::getenv("STK_K2_STREAM_HINT");
-      hint = e ? std::atoi(e) : 0;
-    }
-    p.stream_hint = hint;
-  }
   p.n_ranges = a->n_ranges;
   p.range_end = a->range_end_vec;
   p.range_group = a->range_group;

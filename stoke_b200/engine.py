@@ -557,6 +557,7 @@ class GradPath:
             self.grad_views.append(gv)
         self._micro = 0
         self._raw_has_acc = False
+        self._bucket_tabs = {}
         # ---- autograd hooks: per-bucket launches while backward runs, and unused-parameter detection ----
         self.overlap = bool(overlap) and W > 1 and len(self.buckets) > 1
         self._comm_stream = torch.cuda.Stream(engine.device) if self.overlap else None
@@ -651,9 +652,16 @@ class GradPath:
             self._comm_stream.wait_event(ev)
             stream = self._comm_stream
         e.state_select(self.state_id)
-        e.grad_reduce(mode, self.G.peer_ptrs(b0 * esz), self.model_dtype,
-                      self.ACC.peer_ptrs(b0 * 4) if has_acc else None, out_ptrs, torch.float32, b1 - b0, 1.0 / e.world,
-                      self.clip.norm_kind, self.clip.norm_type, flags, stream=stream)
+        # pointer tables per bucket are built once (the hooks run on the autograd thread: keep them short)
+        key = (k, has_acc)
+        tabs = self._bucket_tabs.get(key)
+        if tabs is None:
+            tabs = (_lib.ptr_array(self.G.peer_ptrs(b0 * esz)),
+                    _lib.ptr_array(self.ACC.peer_ptrs(b0 * 4)) if has_acc else None, _lib.ptr_array(out_ptrs))
+            self._bucket_tabs[key] = tabs
+        e._check(e.lib.stk_grad_reduce(e.ctx, mode, tabs[0], _DT[self.model_dtype], tabs[1], tabs[2], _lib.F32, b1 - b0,
+                                       1.0 / e.world, self.clip.norm_kind, self.clip.norm_type, flags, e._stream(stream)))
+        e.launches += 1
 
     def after_backward(self, sync: bool, unscale: bool):
         """Called once per backward.  ``sync=False``: local accumulation (no_sync); ``sync=True``: the reduce of the

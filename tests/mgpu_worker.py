@@ -42,12 +42,12 @@ def main(out_path):
 
     # (name, optimizer, kwargs, model dtype, clip, accum, fairscale_oss, route (None: the default -- sharded), bucket MB)
     cases = [
-        ("ddp_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, False, None, 0.25),
-        ("ddp_adam_fp32_accum2", torch.optim.Adam, {"lr": 1e-3, "weight_decay": 0.01}, None, ("norm", 0.5, 2.0), 2, False, None, 0.5),
+        ("ddp_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, False, None, 0.008),
+        ("ddp_adam_fp32_accum2", torch.optim.Adam, {"lr": 1e-3, "weight_decay": 0.01}, None, ("norm", 0.5, 2.0), 2, False, None, 0.016),
         ("ddp_sgd_bf16_clipvalue", torch.optim.SGD, {"lr": 0.05, "momentum": 0.9}, torch.bfloat16, ("value", 0.2), 1, False, None, 25.0),
-        ("allreduce_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, False, "allreduce", 0.25),
+        ("allreduce_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, False, "allreduce", 0.008),
         ("allreduce_adamw_fp32_accum2", torch.optim.AdamW, {"lr": 1e-3, "weight_decay": 0.05}, None, ("norm", 1.0, 2.0), 2, False, "allreduce", 25.0),
-        ("oss_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, True, None, 0.1),
+        ("oss_adam_bf16_clipnorm", torch.optim.Adam, {"lr": 1e-3}, torch.bfloat16, ("norm", 1.0, 2.0), 1, True, None, 0.008),
         ("oss_adamw_fp32_accum3_inf", torch.optim.AdamW, {"lr": 1e-3, "weight_decay": 0.05}, None,
          ("norm", 2.0, float("inf")), 3, True, None, 25.0),
     ]

@@ -19,11 +19,16 @@ def _run(world, tmp_path, port, algo="ldg"):
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), str(out)]
     # cross-rank K1 flavour: register-staged loads | bulk-async through smem | multimem (NVLS); tiny gradient buckets in the
     # Stoke-API section so that the per-bucket launches from autograd hooks are exercised on a small model
-    env = dict(os.environ, STK_K1_ALGO=algo, STK_BUCKET_MB="0.0005")
+    env = dict(os.environ, STK_K1_ALGO=algo, STK_BUCKET_MB="0.0005", STK_SPIN_TIMEOUT_S="30")
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     assert proc.returncode == 0, proc.stdout[-4000:] + proc.stderr[-4000:]
     with open(out) as f:
-        return json.load(f)
+        res = json.load(f)
+    keep = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(keep):   # evidence for profiles/: which memory mode / multicast binding each flavour really ran with
+        with open(os.path.join(keep, f"mgpu_w{world}_{algo}.json"), "w") as f:
+            json.dump(res, f, indent=1)
+    return res
 
 
 @pytest.mark.parametrize("algo", ["ldg", "bulk", "nvls"])
@@ -48,5 +53,8 @@ def test_multi_gpu_parity(world, algo, tmp_path):
         assert r["replicas_identical"] and r["buffers_identical"] and r["loss_identical_across_ranks"], (name, r)
         assert r["resume_bit_identical"], (name, r)
         assert r["opt_steps"] == 6 and r["sharded"] and r["buckets"] > 1 and r["overlap"], (name, r)
+    if algo == "nvls" and res["caps"]["multicast"]:
+        # the multimem flavour really ran on multicast-bound buckets (otherwise the call silently fell back to bulk)
+        assert res["kat_full_size"]["mc"] and res["ddp_adam_bf16_clipnorm"]["mc"], res["caps"]
     inf = res["inf_skip"]
     assert inf["unchanged"] and inf["scale"] == 128.0 and inf["skipped"] == 1 and inf["steps"] == 0
