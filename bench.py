@@ -276,10 +276,13 @@ def build_workload(args, sb, torch, local_rank, world, rank):
         feed = iter(DevicePrefetcher(host_batches()))  # what StokeDataLoader uses: batch i+1 is copied while i computes
 
         def step_e2e():
+            # every step's synced loss is read back on the host exactly once, one step behind (the value landed in pinned
+            # memory during the previous step; reading it here does not drain the queue of the step being launched)
+            last = s.step_loss
             x, y = next(feed)                   # 77 MB host -> device copy per step, inside the timed region
             s.backward(s.loss(s.model(x), y))
             s.step()
-            return s.step_loss                  # the synced loss is read back to the host every step (8 B, one sync)
+            return last
 
         h2d = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
         return s, step_resident, step_e2e, batch, h2d, WORKLOAD + ("_oss" if common["fairscale_oss"] else ""), {}
@@ -338,10 +341,11 @@ def build_workload(args, sb, torch, local_rank, world, rank):
     feed = iter(DevicePrefetcher(host_batches()))
 
     def step_e2e():
+        last = s.step_loss                      # the previous step's synced loss (see the resnet50 workload)
         ids, mask, y = next(feed)
         s.backward(s.loss(s.model(input_ids=ids, attention_mask=mask).logits, y))
         s.step()
-        return s.step_loss
+        return last
 
     h2d = int(sum(sum(t.numel() * t.element_size() for t in b) for b in pool) / len(pool))
     extras = {"_distinct_shapes": len(seen), "sampler_setup_ms": sampler_ms, "dataset_items": n_items, "buckets": 16,
@@ -442,6 +446,7 @@ def main():
         tot, cnt = eng.profile_read(kind)
         ev[key] = (tot, cnt)
     k1_dev_ms, k1_dev_n, k1_zero_ms = eng.profile_read_k1_device()
+    k2_dev_ms, k2_dev_n = eng.profile_read_k2_device()
     eng.profile(False)
 
     # ---- timed region 2: end to end (H2D of the batch + D2H of the loss inside the timed region) ----
@@ -503,14 +508,19 @@ def main():
                          "ms_per_launch_events": per_launch("k1"), "ms_zero_tail": k1_zero_ms / k1_launches, "peak": 900.0,
                          "timer": "device timer between K1's start and end barriers (the NVLink phase); events also listed",
                          "traffic": None}
-        kernels["k2"] = {"kernel": k2_name, "bound": k2_bound, "bytes_per_launch": k2_bytes, "ms_per_launch": per_launch("k2"),
-                         "peak": k2_peak, "traffic": None}
+        kernels["k2"] = {"kernel": k2_name, "bound": k2_bound, "bytes_per_launch": k2_bytes,
+                         "ms_per_launch": (k2_dev_ms / k2_dev_n) if (path.sharded and k2_dev_n) else per_launch("k2"),
+                         "ms_per_launch_events": per_launch("k2"), "peak": k2_peak, "traffic": None}
+        if path.sharded:
+            kernels["k2"]["timer"] = "device timer between the sharded step's barriers (local update + parameter all-gather); " \
+                                     "events (which include the wait for the slowest rank to arrive) also listed"
     for k in kernels.values():
         k["achieved"] = k["bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9 if k["ms_per_launch"] else None
         k["unit"] = "GB/s"
         k["frac"] = k["achieved"] / k["peak"] if k["achieved"] else None
         k["peak_source"] = hbm_src if k["bound"] == "hbm" else "NVLink 5 nominal per direction (measured peer copy 770 GB/s)"
-    step_ms = {"k1": (k1_dev_ms / steps) if world > 1 else per_step("norm"), "k2": per_step("k2")}
+    step_ms = {"k1": (k1_dev_ms / steps) if world > 1 else per_step("norm"),
+               "k2": (k2_dev_ms / steps) if (world > 1 and path.sharded and k2_dev_n) else per_step("k2")}
     dominant = max(kernels, key=lambda k: step_ms.get(k, 0.0))
     roofline = dict(kernels[dominant])
     roofline["dominant_by"] = "largest share of the step among the engine's kernels (ms per step: " + \
@@ -534,7 +544,9 @@ def main():
                             "l2": "per-step working set (activations, 0.9 GB of optimizer state) exceeds the 126 MB L2; no flush"},
                            **extras),
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": METRIC, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+                    "note": "batch copied from pinned host memory by the prefetcher every step; the synced loss of step i is written "
+                            "to pinned host memory by the loss kernel and read by the host while step i+1 is being launched"},
             "gpu_launches": launches, "clocks": clock_info, "roofline": roofline}
     if parity is not None:
         line["parity_check"] = parity

@@ -165,6 +165,9 @@ int stk_profile_read(stk_ctx* ctx, int kind, double* ms_total, int* launches);
  * excludes the wait for the slowest rank to arrive, which host-side events include; ms_zero_tail (may be NULL) receives
  * the time block 0 then spent zeroing its part of the local bucket (HBM work).  Synchronises `stream`. */
 int stk_profile_read_k1_device(stk_ctx* ctx, double* ms_total, int* launches, double* ms_zero_tail, void* stream);
+/* the same for the sharded optimizer step (cross-rank K2): time between its start and end barriers = local update + the
+ * parameter all-gather, without the wait for the slowest rank to arrive.  Synchronises `stream`. */
+int stk_profile_read_k2_device(stk_ctx* ctx, double* ms_total, int* launches, void* stream);
 
 /* ---- scaler / step state ------------------------------------------------------------------------------------------- */
 /* One device-resident state (loss scaler, found_inf, grad_norm, step counters, per-step norm accumulators) per optimizer.

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "stk_profile_enable": (C.c_int, [_P, C.c_int]),
     "stk_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "stk_profile_read_k1_device": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double), _P]),
+    "stk_profile_read_k2_device": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int), _P]),
     "stk_scaler_set": (C.c_int, [_P, C.POINTER(ScalerState), _P]),
     "stk_scaler_get": (C.c_int, [_P, C.POINTER(ScalerState), _P]),
     "stk_scaler_scale_ptr": (_P, [_P]),

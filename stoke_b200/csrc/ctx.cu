@@ -64,6 +64,8 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
     c->k1_algo = (std::strcmp(algo, "nvls") == 0) ? 2 : (std::strcmp(algo, "bulk") == 0) ? 1 : 0;
   if (const char* v = std::getenv("STK_K1_MAX_BLOCKS")) c->k1_max_blocks = std::atoi(v);
   if (const char* v = std::getenv("STK_COOP_LAUNCH")) c->coop_launch = std::atoi(v) != 0;
+  if (const char* v = std::getenv("STK_NVLS_MAX_BLOCKS")) c->nvls_max_blocks = std::atoi(v);
+  if (const char* v = std::getenv("STK_K2_AG")) c->k2_ag_mc = std::strcmp(v, "mc") == 0;
   // memory back end: VMM (needed for NVLS multicast) when there are peers and the driver supports it
   bool mc = false;
   const bool vmm = stk_vmm_available(device, &mc);
@@ -75,8 +77,8 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
   }
   if (c->mem_mode == 0) c->multicast_ok = false;
   cudaError_t e;
-  if ((e = cudaMalloc(&c->prof_ns_dev, 4 * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(c->prof_ns_dev, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+  if ((e = cudaMalloc(&c->prof_ns_dev, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(c->prof_ns_dev, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaHostAlloc(&c->host_scratch, sizeof(double) * 16, cudaHostAllocMapped)) != cudaSuccess ||
       (e = cudaHostGetDevicePointer(&c->host_scratch_dev, c->host_scratch, 0)) != cudaSuccess ||
       (e = cudaHostAlloc(&c->loss_ring, sizeof(double) * STK_LOSS_RING, cudaHostAllocMapped)) != cudaSuccess ||
@@ -488,6 +490,20 @@ int stk_profile_read_k1_device(stk_ctx* c, double* ms_total, int* launches, doub
   *ms_total = (double)v[0] * 1e-6;
   *launches = (int)v[1];
   if (ms_zero_tail) *ms_zero_tail = (double)v[2] * 1e-6;
+  return STK_OK;
+}
+
+int stk_profile_read_k2_device(stk_ctx* c, double* ms_total, int* launches, void* stream) {
+  STK_REQUIRE(c, c && ms_total && launches, "stk_profile_read_k2_device: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long v[2] = {0, 0};
+  STK_CUDA(c, cudaMemcpyAsync(v, c->prof_ns_dev + 4, sizeof(v), cudaMemcpyDeviceToHost, s));
+  STK_CUDA(c, cudaMemsetAsync(c->prof_ns_dev + 4, 0, sizeof(v), s));
+  STK_CUDA(c, cudaStreamSynchronize(s));
+  *ms_total = (double)v[0] * 1e-6;
+  *launches = (int)v[1];
   return STK_OK;
 }
 

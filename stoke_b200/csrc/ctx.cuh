@@ -58,6 +58,8 @@ struct stk_ctx {
   int k1_algo = 1;              // cross-rank K1 flavour: 0 = register-staged loads, 1 = bulk-async (default), 2 = multimem (NVLS)
   int k1_max_blocks = 0;        // 0: one block per SM
   int coop_launch = 1;
+  int nvls_max_blocks = 0;      // grid bound of the multimem flavour (0: like the other flavours)
+  int k2_ag_mc = 0;             // sharded step publishes its shard with multimem.st (one store replicated by the switch)
   // device state
   std::vector<StepState> states;      // [0] is created with the context
   int cur_state = 0;

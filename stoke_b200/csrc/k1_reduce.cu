@@ -254,7 +254,8 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
     p.grad_mc = stk_mc_lookup(c, grad_ptrs[c->rank]);
     p.out_mc = (mode == STK_REDUCE_ALL) ? stk_mc_lookup(c, out_ptrs[c->rank]) : nullptr;
     if (p.grad_mc && (mode == STK_REDUCE_SCATTER || p.out_mc)) {
-      err = launch_reduce_nvls(c, p, grad_dtype, out_dtype, grid, s);
+      const int ngrid = c->nvls_max_blocks > 0 ? std::min(grid, c->nvls_max_blocks) : grid;
+      err = launch_reduce_nvls(c, p, grad_dtype, out_dtype, ngrid, s);
       if (err != cudaSuccess && err != cudaErrorNotSupported)
         return stk_fail(c, STK_ERR_CUDA, std::string("k_grad_reduce_nvls launch: ") + cudaGetErrorString(err));
     }

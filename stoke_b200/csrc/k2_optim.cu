@@ -39,6 +39,8 @@ struct OptimParams {
   const float* acc;     // RAW only
   size_t nvec;          // 8-float vector count of the local state
   PtrTable lp;          // low-precision / remote parameter destinations (bases; indexed globally)
+  void* lp_mc;          // multicast mapping of the parameter buffer: publish with ONE multimem.st instead of W peer stores
+  unsigned long long* prof_ns;  // optional {ns between the barriers, launches} (block 0), nullptr when off
   int lp_world;         // 0: none
   int lp_rank_skip;     // lp dtype == f32 and destination == master's own buffer: skip that rank (aliased)
   const stk_scaler_state_t* scaler;
@@ -91,6 +93,13 @@ __device__ __forceinline__ void store_lp(const OptimParams& p, size_t gv, const 
     for (int k = 0; k < VPT; ++k)
       u[k] = make_uint4(pack_bf16(x[k][0], x[k][1]), pack_bf16(x[k][2], x[k][3]), pack_bf16(x[k][4], x[k][5]),
                         pack_bf16(x[k][6], x[k][7]));
+    if (p.lp_mc != nullptr) {
+      // the NVSwitch replicates the store into every rank's parameter buffer (this rank's own copy included)
+#pragma unroll
+      for (int k = 0; k < VPT; ++k)
+        if (k < nv) mm_st16(reinterpret_cast<uint4*>(p.lp_mc) + gv + k, u[k]);
+      return;
+    }
 #pragma unroll 1
     for (int d = 0; d < p.lp_world; ++d) {
       const int dst = p.lp_world == 1 ? 0 : (p.rank + d) % p.lp_world;
@@ -126,6 +135,8 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
   __shared__ int s_skip, s_first;
   __shared__ float s_inv_scale;
   if (PERSIST && p.cross_rank && !block_barrier_all_ranks(p.pads, p.rank, p.world, 0, p.epoch)) return;
+  unsigned long long t_begin = 0;
+  if (PERSIST && p.prof_ns && blockIdx.x == 0 && threadIdx.x == 0) t_begin = globaltimer_ns();
 
   const bool use_m = (KIND != STK_OPT_SGD) || p.m != nullptr;
   const size_t stride = PERSIST ? size_t(gridDim.x) * blockDim.x * VPT : 0;
@@ -266,6 +277,10 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
     load();
   }
   if (PERSIST && p.cross_rank) block_barrier_all_ranks(p.pads, p.rank, p.world, 1, p.epoch);
+  if (PERSIST && p.prof_ns && blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&p.prof_ns[0], globaltimer_ns() - t_begin);
+    atomicAdd(&p.prof_ns[1], 1ull);
+  }
 }
 
 // scaler.update() (torch/amp/grad_scaler.py:549-556 -> _amp_update_scale_), step counters, per-step accumulator reset
@@ -334,7 +349,7 @@ static cudaError_t launch_optim(stk_ctx* c, const OptimParams& p, int lp_dtype, 
   }
   if (p.cross_rank) {
     if (lp_dtype == STK_BF16) {
-      if (pair) return launch_one(c, k_optim_step<KIND, STK_BF16, true, 2, STK_F32, false>, p, true, 2, s);
+      if (pair && p.lp_mc == nullptr) return launch_one(c, k_optim_step<KIND, STK_BF16, true, 2, STK_F32, false>, p, true, 2, s);
       return launch_one(c, k_optim_step<KIND, STK_BF16, true, 1, STK_F32, false>, p, true, 1, s);
     }
     return launch_one(c, k_optim_step<KIND, STK_F32, true, 1, STK_F32, false>, p, true, 1, s);
@@ -414,6 +429,9 @@ int stk_optim_step_ex(stk_ctx* c, const stk_optim_args_t* a, void* stream) {
         static_cast<char*>(a->lp_ptrs[r]) + size_t(p.seg_global[0]) * 32 == reinterpret_cast<char*>(a->master))
       p.lp_rank_skip = r;
   }
+  p.lp_mc = nullptr;
+  if (cross && c->k2_ag_mc && a->lp_dtype != STK_F32) p.lp_mc = stk_mc_lookup(c, a->lp_ptrs[c->rank]);  // nullptr: not bound
+  p.prof_ns = (cross && c->profiling) ? c->prof_ns_dev + 4 : nullptr;
   p.scaler = c->scaler_dev;
   p.pads = c->pads;
   p.rank = c->rank;

@@ -338,6 +338,12 @@ class Engine:
         self._check(self.lib.stk_profile_read_k1_device(self.ctx, C.byref(ms), C.byref(n), C.byref(z), self._stream()))
         return ms.value, n.value, z.value
 
+    def profile_read_k2_device(self):
+        """(ms between the sharded step's start and end barriers, launches) from the device timer."""
+        ms, n = C.c_double(), C.c_int()
+        self._check(self.lib.stk_profile_read_k2_device(self.ctx, C.byref(ms), C.byref(n), self._stream()))
+        return ms.value, n.value
+
     def comm_check(self):
         self._check(self.lib.stk_comm_check(self.ctx, self._stream()))
 
