@@ -189,7 +189,7 @@ def parity_check(eng, rank, world):
     for route in ("allreduce", "sharded"):
         net = Big(RESNET50_PARAMS).to(dev)
         opt = B200FusedOptimizer(net, torch.optim.SGD, {"lr": 0.0}, engine=eng, clip=clip, lp_dtype=torch.bfloat16,
-                                 route=route, bucket_mb=25.0)
+                                 route=route, bucket_mb=8.0)
         path = opt.path
         if route == "allreduce" and path.G.mc_ptr and path.MAIN.mc_ptr:
             flavours.append("nvls")

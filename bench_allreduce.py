@@ -46,11 +46,66 @@ def time_op(fn, warmup=10, iters=50):
     return float(ms.item())
 
 
+def study(args, eng, rank, world, G, O16, O32, have_nvls):
+    """Grid-size studies on this box (each cell: 10 warm-up + 50 timed launches, CUDA events, max over ranks)."""
+    from stoke_b200 import _lib
+
+    lib, ctx = eng.lib, eng.ctx
+    stream = torch.cuda.current_stream().cuda_stream
+    gp, o16, o32 = _lib.ptr_array(G.peer_ptrs()), _lib.ptr_array(O16.peer_ptrs()), _lib.ptr_array(O32.peer_ptrs())
+    out = {"world": world, "nvls_grid": [], "reduce_scatter": [], "allreduce_grid": []}
+
+    def launch(mode, n, outp, odt):
+        rc = lib.stk_grad_reduce(ctx, mode, gp, _lib.BF16, None, outp, odt, n, 1.0 / world, _lib.NORM_L2, 2.0, _lib.RF_FINAL, stream)
+        if rc != 0:
+            _lib.check(rc, ctx)
+
+    # (a) multimem all-reduce (bf16 -> bf16) vs grid
+    if have_nvls:
+        eng.set_k1_algo("nvls")
+        for S in (1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20):
+            if S > args.max_mb << 20:
+                continue
+            for cap in (8, 16, 32, 64, 96, 148):
+                eng.option_set(_lib.OPT_NVLS_MAX_BLOCKS, cap)
+                t = time_op(lambda: launch(_lib.REDUCE_ALL, S // 2, o16, _lib.BF16))
+                out["nvls_grid"].append({"bytes": S, "blocks": cap, "us": t * 1e3, "busbw": 2 * (world - 1) / world * S / (t * 1e-3) / 1e9})
+                if rank == 0:
+                    print(json.dumps(out["nvls_grid"][-1]), flush=True)
+        eng.option_set(_lib.OPT_NVLS_MAX_BLOCKS, 0)
+    # (b) reduce-scatter of a ResNet-50-sized bf16 bucket (the in-step K1 of the sharded route) vs flavour and grid
+    n = 25_557_040
+    for algo in ("bulk", "ldg") + (("nvls",) if have_nvls else ()):
+        eng.set_k1_algo(algo)
+        for cap in (148, 128, 96, 64, 32):
+            eng.option_set(_lib.OPT_K1_MAX_BLOCKS, cap if cap < 148 else 0)
+            t = time_op(lambda: launch(_lib.REDUCE_SCATTER, n, o32, _lib.F32))
+            row = {"algo": algo, "blocks": cap, "us": t * 1e3, "wire_gbs": (world - 1) / world * n * 2 / (t * 1e-3) / 1e9}
+            out["reduce_scatter"].append(row)
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+    # (c) bulk all-reduce (bf16 -> bf16) at 64 MiB vs grid
+    eng.set_k1_algo("bulk")
+    for cap in (148, 96, 64):
+        eng.option_set(_lib.OPT_K1_MAX_BLOCKS, cap if cap < 148 else 0)
+        S = 64 << 20
+        t = time_op(lambda: launch(_lib.REDUCE_ALL, S // 2, o16, _lib.BF16))
+        out["allreduce_grid"].append({"bytes": S, "blocks": cap, "us": t * 1e3, "busbw": 2 * (world - 1) / world * S / (t * 1e-3) / 1e9})
+    eng.option_set(_lib.OPT_K1_MAX_BLOCKS, 0)
+    eng.comm_check()
+    if rank == 0 and args.out:
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-mb", type=int, default=1024)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-baselines", action="store_true", help="skip NCCL / symmetric-memory rows")
+    ap.add_argument("--study", action="store_true",
+                    help="tuning study instead of the sweep: multimem flavour vs grid size, reduce-scatter of a ResNet-50-sized "
+                         "bucket vs flavour and grid size (device-timed); writes --out")
     ap.add_argument("--json-line", action="store_true", help="print ONE bench.py-shaped JSON line (bench.py --workload allreduce_sweep)")
     args = ap.parse_args(argv)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -84,6 +139,12 @@ def main(argv=None):
     except Exception as e:  # noqa: BLE001
         if rank == 0:
             print(f"symm_mem unavailable: {type(e).__name__}: {e}", file=sys.stderr)
+
+    if args.study:
+        study(args, eng, rank, world, G, O16, O32, have_nvls)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     rows = []
     for S in sizes:

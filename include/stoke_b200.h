@@ -153,6 +153,8 @@ int stk_comm_poll(stk_ctx* ctx);
 #define STK_OPT_MEM_MODE 2
 #define STK_OPT_K1_MAX_BLOCKS 3
 #define STK_OPT_COOP_LAUNCH 4   /* 1 (default): cross-rank kernels use cooperative launches (co-residency enforced) */
+#define STK_OPT_NVLS_MAX_BLOCKS 5 /* grid bound of the multimem flavour alone (0: same as STK_OPT_K1_MAX_BLOCKS) */
+#define STK_OPT_K2_AG_MC 6      /* 1: the sharded step publishes its shard with multimem.st when the parameter buffer is bound */
 int stk_option_set(stk_ctx* ctx, int key, int value);
 int stk_option_get(stk_ctx* ctx, int key, int* value);
 

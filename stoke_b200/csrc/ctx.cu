@@ -75,6 +75,8 @@ int stk_ctx_create(int rank, int world, int device, unsigned flags, stk_ctx** ou
     if (std::strcmp(m, "ipc") == 0) c->mem_mode = 0;
     else if (std::strcmp(m, "vmm") == 0 && vmm) c->mem_mode = 1;
   }
+  if (const char* m = std::getenv("STK_MULTICAST"))
+    if (std::atoi(m) == 0) c->multicast_ok = false;   // keep VMM memory but never create / bind multicast objects
   if (c->mem_mode == 0) c->multicast_ok = false;
   cudaError_t e;
   if ((e = cudaMalloc(&c->prof_ns_dev, 8 * sizeof(unsigned long long))) != cudaSuccess ||
@@ -433,6 +435,13 @@ int stk_option_set(stk_ctx* c, int key, int value) {
     case STK_OPT_COOP_LAUNCH:
       c->coop_launch = value != 0;
       return STK_OK;
+    case STK_OPT_NVLS_MAX_BLOCKS:
+      STK_REQUIRE(c, value >= 0 && value <= stk::kMaxReduceBlocks, "stk_option_set: NVLS max blocks out of range");
+      c->nvls_max_blocks = value;
+      return STK_OK;
+    case STK_OPT_K2_AG_MC:
+      c->k2_ag_mc = value != 0;
+      return STK_OK;
     default:
       return stk_fail(c, STK_ERR_INVALID, "stk_option_set: unknown key");
   }
@@ -446,6 +455,8 @@ int stk_option_get(stk_ctx* c, int key, int* value) {
     case STK_OPT_MEM_MODE: *value = c->mem_mode; return STK_OK;
     case STK_OPT_K1_MAX_BLOCKS: *value = c->k1_max_blocks; return STK_OK;
     case STK_OPT_COOP_LAUNCH: *value = c->coop_launch; return STK_OK;
+    case STK_OPT_NVLS_MAX_BLOCKS: *value = c->nvls_max_blocks; return STK_OK;
+    case STK_OPT_K2_AG_MC: *value = c->k2_ag_mc; return STK_OK;
     default: return stk_fail(c, STK_ERR_INVALID, "stk_option_get: unknown key");
   }
 }

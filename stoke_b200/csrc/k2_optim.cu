@@ -18,6 +18,8 @@
 // Arithmetic follows torch/optim/adam.py (_single_tensor_adam, the path torch takes on CPU -- the oracle) and
 // torch/optim/sgd.py (_single_tensor_sgd); the clip follows torch/nn/utils/clip_grad.py:165-174 (coef = max_norm /
 // (total_norm + 1e-6), clamped to 1) and :291-292 (clamp).
+#include <cstdlib>
+
 #include "k1_common.cuh"
 
 namespace stk {
@@ -459,6 +461,14 @@ int stk_optim_step_ex(stk_ctx* c, const stk_optim_args_t* a, void* stream) {
     p.unscale = 1;
   }
 
+  {
+    static int pair_env = -1;   // STK_K2_PAIR=0: one vector per thread in the sharded step (16-byte peer stores, 3 blocks/SM)
+    if (pair_env < 0) {
+      const char* e = std::getenv("STK_K2_PAIR");
+      pair_env = e ? std::atoi(e) : 1;
+    }
+    if (!pair_env) pair_ok = false;
+  }
   cudaError_t err;
   const bool raw = a->grad_raw != 0;
   g_grid_nvec = cross ? (a->grid_n ? (a->grid_n + 7) / 8 : p.nvec) : 0;

@@ -464,6 +464,14 @@ class GradPath:
         if bucket_mb is None:
             bucket_mb = float(os.environ.get("STK_BUCKET_MB", DEFAULT_BUCKET_MB))
         cap = max(int(bucket_mb * (1 << 20) / esz), ALIGN_ELEMS) if W > 1 else self.n
+        # Overlap policy (STK_OVERLAP=auto|on|off).  A reduce launched from an autograd hook shares the GPU with the backward
+        # kernels still running; measured on ResNet-50 (2 buckets of 25 MiB, profiles/scaling_r02.md) that costs more than the
+        # ~30 us it hides, while one launch over the whole buffer after backward is also the most efficient shape for the
+        # wire.  "auto" therefore buckets (and overlaps) only when there are at least 4 buckets' worth of gradients.
+        mode = os.environ.get("STK_OVERLAP", "auto")
+        nominal = (self.n + cap - 1) // cap
+        if W > 1 and (not overlap or mode == "off" or (mode == "auto" and nominal < 4)):
+            cap = self.n
         self.buckets: List[Tuple[int, int]] = []
         hi = self.n
         for i in range(len(self.params) - 1, -1, -1):
@@ -566,6 +574,7 @@ class GradPath:
         self._bucket_tabs = {}
         # ---- autograd hooks: per-bucket launches while backward runs, and unused-parameter detection ----
         self.overlap = bool(overlap) and W > 1 and len(self.buckets) > 1
+        self._overlap_blocks = int(os.environ.get("STK_K1_OVERLAP_BLOCKS", "0")) if self.overlap else 0
         self._comm_stream = torch.cuda.Stream(engine.device) if self.overlap else None
         self._hooks = []
         self._armed = False          # hooks launch K1 for this backward
@@ -658,6 +667,10 @@ class GradPath:
             self._comm_stream.wait_event(ev)
             stream = self._comm_stream
         e.state_select(self.state_id)
+        # grid of this launch: a function of the bucket index only (identical on every rank whatever launched it -- a hook or
+        # the flush after backward): every bucket but the last may run on a reduced grid so that it shares the SMs with backward
+        if self._overlap_blocks:
+            e.option_set(_lib.OPT_K1_MAX_BLOCKS, self._overlap_blocks if k < len(self.buckets) - 1 else 0)
         # pointer tables per bucket are built once (the hooks run on the autograd thread: keep them short)
         key = (k, has_acc)
         tabs = self._bucket_tabs.get(key)
