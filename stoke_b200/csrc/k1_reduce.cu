@@ -254,7 +254,11 @@ int stk_grad_reduce(stk_ctx* c, int mode, void* const* grad_ptrs, int grad_dtype
     p.grad_mc = stk_mc_lookup(c, grad_ptrs[c->rank]);
     p.out_mc = (mode == STK_REDUCE_ALL) ? stk_mc_lookup(c, out_ptrs[c->rank]) : nullptr;
     if (p.grad_mc && (mode == STK_REDUCE_SCATTER || p.out_mc)) {
-      const int ngrid = c->nvls_max_blocks > 0 ? std::min(grid, c->nvls_max_blocks) : grid;
+      // The switch-side reduction saturates with few requesters: measured at W = 8 (profiles/study_w8_r02.json) 8 blocks beat
+      // 148 at every size from 1 MiB to 256 MiB (16 MiB: 501 vs 392 GB/s busbw, 64 MiB: 706 vs 593, 256 MiB: 800 vs 764).
+      const size_t bytes = n * (grad_dtype == STK_F32 ? 4 : 2);
+      const int nvls_default = bytes < (size_t(128) << 20) ? 8 : 16;
+      const int ngrid = std::min(grid, c->nvls_max_blocks > 0 ? c->nvls_max_blocks : nvls_default);
       err = launch_reduce_nvls(c, p, grad_dtype, out_dtype, ngrid, s);
       if (err != cudaSuccess && err != cudaErrorNotSupported)
         return stk_fail(c, STK_ERR_CUDA, std::string("k_grad_reduce_nvls launch: ") + cudaGetErrorString(err));
