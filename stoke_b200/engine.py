@@ -30,12 +30,12 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, layout
 from ._lib import StokeB200Error, check
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 _ESZ = {torch.float32: 4, torch.bfloat16: 2, torch.float16: 2}
-ALIGN_ELEMS = 16  # every parameter starts on a 16-element boundary (32 B of bf16 / 64 B of fp32)
+ALIGN_ELEMS = layout.ALIGN_ELEMS  # every parameter starts on a 16-element boundary (32 B of bf16 / 64 B of fp32)
 DEFAULT_BUCKET_MB = 25.0  # DDPConfig.bucket_cap_mb of the reference (stoke/configs.py:178-188)
 
 
@@ -449,15 +449,8 @@ class GradPath:
         self.state_id = engine.state_create() if state_id is None else state_id
         self._own_state = state_id is None
 
-        # ---- layout ----
-        self.offsets, off = [], 0
-        self.padded = []
-        for p in self.params:
-            self.offsets.append(off)
-            pn = (p.numel() + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
-            self.padded.append(pn)
-            off += pn
-        self.n = off
+        # ---- layout (planned by the pure-Python module layout.py, unit-tested on CPU) ----
+        self.offsets, self.padded, self.n = layout.param_offsets([p.numel() for p in self.params])
         esz = _ESZ[self.model_dtype]
 
         # ---- buckets (launch order: reverse registration order) ----
@@ -472,15 +465,7 @@ class GradPath:
         nominal = (self.n + cap - 1) // cap
         if W > 1 and (not overlap or mode == "off" or (mode == "auto" and nominal < 4)):
             cap = self.n
-        self.buckets: List[Tuple[int, int]] = []
-        hi = self.n
-        for i in range(len(self.params) - 1, -1, -1):
-            if hi - self.offsets[i] >= cap or i == 0:
-                self.buckets.append((self.offsets[i], hi))
-                hi = self.offsets[i]
-        if len(self.buckets) > _lib.MAX_SEGMENTS:  # keep the segment table bounded: merge the tail buckets
-            keep = self.buckets[: _lib.MAX_SEGMENTS - 1]
-            self.buckets = keep + [(0, keep[-1][0])]
+        self.buckets: List[Tuple[int, int]] = layout.plan_buckets(self.offsets, self.n, cap)
         self.param_bucket = [0] * len(self.params)
         for k, (b0, b1) in enumerate(self.buckets):
             for i, o in enumerate(self.offsets):
@@ -489,23 +474,8 @@ class GradPath:
         self.bucket_nparams = [self.param_bucket.count(k) for k in range(len(self.buckets))]
 
         # ---- segments: rank r's shard of every bucket, by ascending element offset ----
-        def segs_of(r):
-            out, lo = [], 0
-            for k in sorted(range(len(self.buckets)), key=lambda k: self.buckets[k][0]):
-                b0, b1 = self.buckets[k]
-                sb, se = engine.shard_range(b1 - b0, r) if self.sharded else (0, b1 - b0)
-                if se > sb:
-                    out.append((b0 + sb, b0 + se, lo, k))
-                    lo += se - sb
-            return out, lo
-
-        if self.sharded:
-            all_segs = [segs_of(r) for r in range(W)]
-            self.segs_by_rank = [s for s, _ in all_segs]
-            self.n_local_by_rank = [n for _, n in all_segs]
-        else:
-            self.segs_by_rank = [[(0, self.n, 0, 0)]] * W
-            self.n_local_by_rank = [self.n] * W
+        self.segs_by_rank, self.n_local_by_rank = layout.plan_segments(
+            self.buckets, W, self.sharded, shard_fn=lambda n_, w_, r_: engine.shard_range(n_, r_))
         self.segs = self.segs_by_rank[engine.rank]
         self.n_local = self.n_local_by_rank[engine.rank]
         self.n_local_max = max(self.n_local_by_rank)

@@ -174,3 +174,33 @@ def test_multiple_losses_bookkeeping_matches_live_reference(fake_stoke, referenc
     a = torch.cat([p.detach().reshape(-1) for p in m_ref.parameters()])
     b = torch.cat([p.detach().reshape(-1) for p in m_new.parameters()])
     assert torch.equal(a, b)
+
+
+def test_lazy_loss_queue_folds_in_order(fake_stoke):
+    """With a runner that offers ``sync_loss_begin`` / ``sync_loss_wait`` (the engine's pinned ring) ``Stoke.loss`` only queues
+    tickets; ``step_loss`` / ``ema_loss`` / the accumulated loss fold them in order -- including the accumulated-loss resets
+    that ``step()`` interleaves -- and equal the eager bookkeeping."""
+    def run(lazy):
+        model = synthetic.basic_nn()
+        s, runner = fake_stoke(model, 3)
+        waits = []
+        if lazy:
+            store = {}
+            runner.sync_loss_begin = lambda loss: store.setdefault(len(store), loss.item()) and len(store) - 1 or len(store) - 1
+            runner.sync_loss_wait = lambda t: (waits.append(t), store[t])[1]
+        seen = []
+        for i, (x, y) in enumerate(synthetic.cfg1_batches(200)):
+            l = s.loss(s.model(x), y)
+            s.backward(l)
+            s.step()
+            if not lazy or i % 50 == 49:
+                seen.append((i, s.step_loss, s.ema_loss, s._agg_loss))
+        return s, seen, waits
+
+    s_eager, eager, _ = run(False)
+    s_lazy, lazy, waits = run(True)
+    assert waits == sorted(waits) and len(waits) == 200            # every ticket waited once, in order
+    by_step = {i: rest for i, *rest in eager}
+    for i, *rest in lazy:
+        assert rest == by_step[i]
+    assert s_lazy._rolling_loss_steps == s_eager._rolling_loss_steps == 200
