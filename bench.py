@@ -374,9 +374,14 @@ def main():
         return
 
     if args.workload == "allreduce_sweep":
+        if world < 2:
+            if rank == 0:
+                print(json.dumps({"metric": "fused grad all-reduce bus bandwidth", "unavailable":
+                                  "configs[4] needs at least 2 GPUs: launch with torch.distributed.run --nproc-per-node N"}))
+            return
         import bench_allreduce
 
-        bench_allreduce.main(["--json-line"] + ([] if world > 1 else []))
+        bench_allreduce.main(["--json-line"])
         return
 
     import torch

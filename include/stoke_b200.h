@@ -247,8 +247,18 @@ typedef struct {
   int n_ranges; const uint32_t* range_end_vec; const uint8_t* range_group;  /* DEVICE arrays; ends in units of 8 elements */
   size_t grid_n;   /* cross-rank (lp_world > 1) launches: the LARGEST n_local over the ranks, identical on every rank, so that
                       every rank launches the same grid (the block barriers pair block b with block b); 0: n_local */
+  const float* range_bc;  /* DEVICE, 4 floats per range {step_size, bias_correction2_sqrt, first_step, 0} written by
+                             stk_optim_range_prologue: per-PARAMETER step counts (torch keeps `step` per parameter, so a
+                             parameter that skipped some steps has its own bias corrections); NULL: the optimizer-wide
+                             counter of the selected state is used for every range */
 } stk_optim_args_t;
 int stk_optim_step_ex(stk_ctx* ctx, const stk_optim_args_t* args, void* stream);
+/* Per-range step bookkeeping for stk_optim_step_ex (call it right before, same stream): for every range j computes the
+ * bias corrections of step range_steps[j] + 1 with its group's hyper-parameters into range_bc[4j..4j+3] and, unless the range
+ * is skipped this step (bit 7 of range_group[j]) or the selected state says found_inf, increments range_steps[j].
+ * All three arrays live in device memory. */
+int stk_optim_range_prologue(stk_ctx* ctx, const stk_optim_hyper_t* hyper, int n_groups, int n_ranges,
+                             const uint8_t* range_group, int32_t* range_steps, float* range_bc, void* stream);
 
 /* scaler.update(), opt_steps/skipped_steps bookkeeping, reset of the per-step accumulators */
 int stk_step_epilogue(stk_ctx* ctx, void* stream);

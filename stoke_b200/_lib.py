@@ -55,7 +55,7 @@ class OptimArgs(C.Structure):
                 ("lp_ptrs", C.POINTER(C.c_void_p)), ("lp_world", C.c_int), ("lp_dtype", C.c_int), ("lp_offset", C.c_size_t),
                 ("n_seg", C.c_int), ("seg_local", C.POINTER(C.c_size_t)), ("seg_global", C.POINTER(C.c_size_t)),
                 ("n_ranges", C.c_int), ("range_end_vec", C.c_void_p), ("range_group", C.c_void_p),
-                ("grid_n", C.c_size_t)]
+                ("grid_n", C.c_size_t), ("range_bc", C.c_void_p)]
 
 
 class SamplerPlan(C.Structure):
@@ -106,6 +106,7 @@ _SIGNATURES = {
     "stk_optim_step": (C.c_int, [_P, C.POINTER(OptimHyper), _P, _P, _P, _P, C.c_size_t, _PP, C.c_int, C.c_int,
                                  C.c_size_t, _P]),
     "stk_optim_step_ex": (C.c_int, [_P, C.POINTER(OptimArgs), _P]),
+    "stk_optim_range_prologue": (C.c_int, [_P, C.POINTER(OptimHyper), C.c_int, C.c_int, _P, _P, _P, _P]),
     "stk_step_epilogue": (C.c_int, [_P, _P]),
     "stk_loss_sync": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
     "stk_loss_sync_begin": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int64), _P]),

@@ -63,6 +63,7 @@ struct OptimParams {
   int n_ranges;                              // 0: group 0 everywhere
   const uint32_t* range_end;                 // device, ascending, vector units (global)
   const uint8_t* range_group;                // device; bit 7: skip
+  const float4* range_bc;                    // device, optional: per-range {step_size, bc2_sqrt, first_step, 0}
 };
 
 // local vector index -> global vector index
@@ -76,15 +77,15 @@ __device__ __forceinline__ size_t to_global(const OptimParams& p, size_t i) {
   }
   return p.seg_global[lo] + (i - p.seg_local[lo]);
 }
-// global vector index -> range byte (group | skip bit)
-__device__ __forceinline__ unsigned range_of(const OptimParams& p, size_t gv) {
+// global vector index -> range index (first j with range_end[j] > gv)
+__device__ __forceinline__ int range_of(const OptimParams& p, size_t gv) {
   int lo = 0, hi = p.n_ranges - 1;
-  while (lo < hi) {  // first j with range_end[j] > gv
+  while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (__ldg(&p.range_end[mid]) > gv) hi = mid;
     else lo = mid + 1;
   }
-  return __ldg(&p.range_group[lo]);
+  return lo;
 }
 
 template <int LP_DT, int VPT>  // -1: none, STK_BF16, STK_F32;  VPT vectors (8 elements each), adjacent in memory
@@ -218,8 +219,19 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
 
   while (nv > 0) {
     unsigned rb = 0;
-    if (p.n_ranges > 0) rb = range_of(p, gv);  // the VPT vectors of a thread never straddle a parameter (16-element alignment)
-    const GroupHyperS h = s_g[rb & 0x7f];
+    float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.n_ranges > 0) {  // the VPT vectors of a thread never straddle a parameter (16-element alignment)
+      const int rj = range_of(p, gv);
+      rb = __ldg(&p.range_group[rj]);
+      if (p.range_bc != nullptr) bc = __ldg(&p.range_bc[rj]);
+    }
+    GroupHyperS h = s_g[rb & 0x7f];
+    bool first_here = first_step;
+    if (p.range_bc != nullptr) {  // per-parameter step counts (torch's `state[p]["step"]`)
+      h.step_size = bc.x;
+      h.bc2_sqrt = bc.y;
+      first_here = bc.z != 0.f;
+    }
     const bool skip = skip_all || (rb & 0x80u);
     if (!skip) {
 #pragma unroll
@@ -250,7 +262,7 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
           } else {  // SGD
             if (h.wd != 0.f) gg = fmaf(ww, h.wd, gg);
             if (h.mom != 0.f) {
-              const float bb = first_step ? gg : fmaf(m[k][e], h.mom, h.one_m_damp * gg);
+              const float bb = first_here ? gg : fmaf(m[k][e], h.mom, h.one_m_damp * gg);
               m[k][e] = bb;
               gg = h.nesterov ? fmaf(bb, h.mom, gg) : bb;
             }
@@ -283,6 +295,33 @@ __global__ void __launch_bounds__(256) k_optim_step(const OptimParams p) {
     atomicAdd(&p.prof_ns[0], globaltimer_ns() - t_begin);
     atomicAdd(&p.prof_ns[1], 1ull);
   }
+}
+
+struct RangePrologueParams {
+  GroupHyperD g[STK_MAX_GROUPS];
+  int n_ranges, kind;
+  const uint8_t* range_group;
+  int32_t* range_steps;
+  float4* range_bc;
+  const stk_scaler_state_t* scaler;
+};
+
+// one thread per range: bias corrections of that range's NEXT step (double, like the python scalars of torch/optim/adam.py)
+// and the step count itself (torch increments state[p]["step"] only for parameters that are stepped)
+__global__ void k_range_prologue(const RangePrologueParams p) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.n_ranges) return;
+  const unsigned b = p.range_group[j];
+  const GroupHyperD& h = p.g[b & 0x7f];
+  const int32_t done = p.range_steps[j];
+  const double t = (double)(done + 1);
+  float4 o = make_float4(0.f, 1.f, done == 0 ? 1.f : 0.f, 0.f);
+  if (p.kind != STK_OPT_SGD) {
+    o.x = (float)(h.lr / (1.0 - pow(h.beta1, t)));
+    o.y = (float)sqrt(1.0 - pow(h.beta2, t));
+  }
+  p.range_bc[j] = o;
+  if (!(b & 0x80u) && p.scaler->found_inf == 0) p.range_steps[j] = done + 1;
 }
 
 // scaler.update() (torch/amp/grad_scaler.py:549-556 -> _amp_update_scale_), step counters, per-step accumulator reset
@@ -456,6 +495,7 @@ int stk_optim_step_ex(stk_ctx* c, const stk_optim_args_t* a, void* stream) {
   p.n_ranges = a->n_ranges;
   p.range_end = a->range_end_vec;
   p.range_group = a->range_group;
+  p.range_bc = a->n_ranges > 0 ? reinterpret_cast<const float4*>(a->range_bc) : nullptr;
   if (a->grad_raw) {
     // 1/loss_scale is applied when the scaler is live; the device flag decides (enabled), so no host read
     p.unscale = 1;
@@ -501,6 +541,31 @@ int stk_optim_step(stk_ctx* c, const stk_optim_hyper_t* h, float* master, float*
   a.lp_dtype = lp_dtype;
   a.lp_offset = lp_offset;
   return stk_optim_step_ex(c, &a, stream);
+}
+
+int stk_optim_range_prologue(stk_ctx* c, const stk_optim_hyper_t* h, int n_groups, int n_ranges, const uint8_t* range_group,
+                             int32_t* range_steps, float* range_bc, void* stream) {
+  STK_REQUIRE(c, c && h && range_group && range_steps && range_bc, "stk_optim_range_prologue: NULL argument");
+  STK_REQUIRE(c, n_groups >= 1 && n_groups <= STK_MAX_GROUPS, "stk_optim_range_prologue: n_groups must be in [1, 8]");
+  STK_REQUIRE(c, n_ranges >= 1, "stk_optim_range_prologue: no ranges");
+  STK_REQUIRE(c, (reinterpret_cast<uintptr_t>(range_bc) & 15) == 0, "stk_optim_range_prologue: range_bc must be 16-byte aligned");
+  std::lock_guard<std::mutex> lk(c->mu);
+  DeviceGuard g(c->device);
+  RangePrologueParams p{};
+  for (int gi = 0; gi < n_groups; ++gi) {
+    GroupHyperD& o = p.g[gi];
+    o.lr = h[gi].lr; o.beta1 = h[gi].beta1; o.beta2 = h[gi].beta2; o.eps = h[gi].eps; o.weight_decay = h[gi].weight_decay;
+    o.momentum = h[gi].momentum; o.dampening = h[gi].dampening; o.nesterov = h[gi].nesterov; o.maximize = h[gi].maximize;
+  }
+  p.n_ranges = n_ranges;
+  p.kind = h->kind;
+  p.range_group = range_group;
+  p.range_steps = range_steps;
+  p.range_bc = reinterpret_cast<float4*>(range_bc);
+  p.scaler = c->scaler_dev;
+  k_range_prologue<<<(n_ranges + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  STK_CUDA(c, cudaGetLastError());
+  return STK_OK;
 }
 
 int stk_step_epilogue(stk_ctx* c, void* stream) {

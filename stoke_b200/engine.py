@@ -527,6 +527,8 @@ class GradPath:
         self._range_end = torch.from_numpy(ends.astype(np.uint32).view(np.int32)).to(dev)
         self._range_group = torch.tensor(self.group_of, dtype=torch.uint8).to(dev)
         self._range_skip_live = False   # the device table currently carries skip bits
+        self._range_steps = None        # int32 per parameter once per-parameter step counts are on (enable_per_param_steps)
+        self._range_bc = None
         self._touched = np.ones(len(self.params), dtype=bool)
         self._track_touched = False
 
@@ -692,7 +694,11 @@ class GradPath:
         some parameter received no gradient in this accumulation window (torch skips ``p.grad is None``)."""
         skip = self._track_touched and not bool(self._touched.all())
         multi = max(self.group_of) > 0
-        if not skip and not multi:
+        if skip and self._range_steps is None:
+            # From the first skipped parameter on, step counts are kept per parameter (torch: state[p]["step"]); until then
+            # every parameter has taken exactly the optimizer-wide number of steps.
+            self.enable_per_param_steps()
+        if not skip and not multi and self._range_steps is None:
             return 0, None, None
         if skip or self._range_skip_live:
             tab = np.asarray(self.group_of, dtype=np.uint8) | np.where(self._touched | (not skip), 0, 0x80).astype(np.uint8)
@@ -700,6 +706,21 @@ class GradPath:
             self._range_group.copy_(torch.from_numpy(tab))
             self._range_skip_live = skip
         return len(self.params), self._range_end.data_ptr(), self._range_group.data_ptr()
+
+    def enable_per_param_steps(self, steps: Optional[Sequence[int]] = None):
+        """Switches the fused step to per-parameter step counts (one synchronisation to read the optimizer-wide count)."""
+        dev = self._range_end.device
+        if steps is None:
+            done = int(self.engine.scaler_get(self.state_id).opt_steps)
+            steps = [done] * len(self.params)
+        self._range_steps = torch.tensor(list(steps), dtype=torch.int32, device=dev)
+        self._range_bc = torch.zeros(len(self.params), 4, dtype=torch.float32, device=dev)
+
+    def param_steps(self) -> List[int]:
+        """Steps taken by every parameter (what torch reports as ``state[p]["step"]``)."""
+        if self._range_steps is None:
+            return [int(self.engine.scaler_get(self.state_id).opt_steps)] * len(self.params)
+        return [int(v) for v in self._range_steps.cpu().tolist()]
 
     def optimizer_step(self, hypers):
         """One fused K2 launch (+ the one-thread epilogue).  ``hypers``: one ``OptimHyper`` or a list (one per group)."""
@@ -745,6 +766,11 @@ class GradPath:
             a.lp_ptrs, a.lp_world, a.lp_dtype = None, 0, _lib.F32
         nr, rend, rgrp = self._ranges_for_step()
         a.n_ranges, a.range_end_vec, a.range_group = nr, rend, rgrp
+        if nr and self._range_steps is not None:
+            e._check(e.lib.stk_optim_range_prologue(e.ctx, harr, ng, nr, rgrp, self._range_steps.data_ptr(),
+                                                    self._range_bc.data_ptr(), e._stream()))
+            e.launches += 1
+            a.range_bc = self._range_bc.data_ptr()
         e.optim_step_ex(a)
         e.step_epilogue()
         self._track_touched = False

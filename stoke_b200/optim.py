@@ -159,14 +159,14 @@ class B200FusedOptimizer(torch.optim.Optimizer):
         state = {}
         ms = path.unflatten(m) if m is not None else None
         vs = path.unflatten(v) if v is not None else None
+        steps = path.param_steps() if path._range_steps is not None else [int(st.opt_steps)] * len(path.params)
         for i in range(len(path.params)):
             j = self._sd_index[i]
             if self._kind == _lib.OPT_SGD:
                 # torch creates the buffer on the first step; before that (or without momentum) it is None
-                state[j] = {"momentum_buffer": ms[i].clone() if ms is not None and st.opt_steps > 0 else None}
+                state[j] = {"momentum_buffer": ms[i].clone() if ms is not None and steps[i] > 0 else None}
             else:
-                state[j] = {"step": torch.tensor(float(st.opt_steps)), "exp_avg": ms[i].clone(),
-                            "exp_avg_sq": vs[i].clone()}
+                state[j] = {"step": torch.tensor(float(steps[i])), "exp_avg": ms[i].clone(), "exp_avg_sq": vs[i].clone()}
         groups, start = [], 0
         for g in self.param_groups:
             d = {k: val for k, val in g.items() if k != "params"}
@@ -205,8 +205,14 @@ class B200FusedOptimizer(torch.optim.Optimizer):
         else:
             put(path.m_flat, "exp_avg")
             put(path.v_flat, "exp_avg_sq")
-            if "b200_opt_steps" not in sd and n and 0 in state:
-                steps = int(float(state[0]["step"]))
+            per_param = [int(float(state[self._sd_index[i]]["step"])) if self._sd_index[i] in state and "step" in state[self._sd_index[i]]
+                         else None for i in range(n)]
+            known = [v for v in per_param if v is not None]
+            if "b200_opt_steps" not in sd and known:
+                steps = max(known)
+            if known and (len(set(known)) > 1 or len(known) < n):
+                # parameters stepped a different number of times (some were unused for a while): keep torch's per-parameter counts
+                path.enable_per_param_steps([steps if v is None else v for v in per_param])
         if "b200_master" in sd:
             master = sd["b200_master"].to(device=dev, dtype=torch.float32)
             if path.master_flat is not path.p_flat:

@@ -414,10 +414,9 @@ def test_parameter_groups_parity(lp):
 
 def test_unused_parameters_are_skipped_like_torch():
     """A parameter that receives no gradient in a step keeps its value AND its optimizer state (torch skips p.grad is None
-    after zero_grad(set_to_none=True), stoke/utils.py:103-106) -- no moment decay, no weight decay.  Parameters that are
-    always used follow the oracle to 1e-5; for the sometimes-unused head the skip itself is checked bit-exactly (its Adam
-    bias correction keeps using the optimizer-wide step count -- torch counts steps per parameter -- a documented
-    deviation that vanishes as the corrections approach 1)."""
+    after zero_grad(set_to_none=True), stoke/utils.py:103-106) -- no moment decay, no weight decay -- and from then on step
+    counts are kept per parameter, like torch's state[p]["step"], so the sometimes-unused head gets its own Adam bias
+    corrections: every parameter follows the oracle to 1e-5."""
     from engine_oracle import OracleEngine
     import stoke_b200 as sb
 
@@ -463,8 +462,26 @@ def test_unused_parameters_are_skipped_like_torch():
             torch.equal(b_before[1], s.optimizer.state_dict()["state"][4]["exp_avg"])
         assert same == (not model.use_b)
     got = [p.detach().float().cpu() for p in model.parameters()]
-    for a, b in list(zip(got, oracle.weights()))[:4]:   # body.weight, body.bias, a.weight, a.bias: always used
+    for a, b in zip(got, oracle.weights()):
         assert _rel(a.reshape(-1), b.reshape(-1)) < TOL
+    sd = s.optimizer.state_dict()
+    for j, p in enumerate(oracle.params):   # per-parameter step counts: 9 for the always-used parameters, 6 for head b
+        assert float(sd["state"][j]["step"]) == float(oracle.optimizer.state[p]["step"])
+    assert [float(sd["state"][j]["step"]) for j in range(6)] == [9.0, 9.0, 9.0, 9.0, 6.0, 6.0]
+    # round trip: a second Stoke loads the per-parameter counts and continues identically
+    model2 = TwoHeads()
+    s2 = sb.Stoke(model=model2, optimizer=sb.StokeOptimizer(optimizer=torch.optim.Adam, optimizer_kwargs=kw),
+                  loss=torch.nn.MSELoss(), batch_size_per_device=8, gpu=True, verbose=False)
+    model2.load_state_dict(model.state_dict())
+    s2.optimizer.load_state_dict(sd)
+    assert s2.optimizer.path.param_steps() == [9, 9, 9, 9, 6, 6]
+    for st, mdl in ((s, model), (s2, model2)):
+        mdl.use_b = True
+        x, y = torch.ones(8, 16).cuda(), torch.ones(8, 1).cuda()
+        st.backward(st.loss(st.model(x), y))
+        st.step()
+    for a, b in zip(model.parameters(), model2.parameters()):
+        assert torch.equal(a.detach(), b.detach())
 
 
 @pytest.mark.parametrize("optim_cls,kwargs,lp,clip", [
