@@ -155,6 +155,10 @@ int stk_comm_poll(stk_ctx* ctx);
 #define STK_OPT_COOP_LAUNCH 4   /* 1 (default): cross-rank kernels use cooperative launches (co-residency enforced) */
 #define STK_OPT_NVLS_MAX_BLOCKS 5 /* grid bound of the multimem flavour alone (0: same as STK_OPT_K1_MAX_BLOCKS) */
 #define STK_OPT_K2_AG_MC 6      /* 1: the sharded step publishes its shard with multimem.st when the parameter buffer is bound */
+#define STK_OPT_K1_ONE_SHOT_KB 7 /* all-reduce buckets of at most this many KiB of input take the ONE-SHOT form: every rank reads
+                                    the whole bucket from all W peers and reduces all of it itself (W x the loads, but no peer
+                                    stores, no store-completion fence, no cross-rank partial exchange: the small-message
+                                    latency path).  Default 256; 0 = always two-shot.  Same results (rank-order fp32 sums). */
 int stk_option_set(stk_ctx* ctx, int key, int value);
 int stk_option_get(stk_ctx* ctx, int key, int* value);
 
