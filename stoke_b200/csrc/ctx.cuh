@@ -59,7 +59,8 @@ struct stk_ctx {
   int k1_max_blocks = 0;        // 0: one block per SM
   int coop_launch = 1;
   int nvls_max_blocks = 0;      // grid bound of the multimem flavour (0: like the other flavours)
-  size_t one_shot_bytes = size_t(256) << 10;  // all-reduce buckets up to this many input bytes take the one-shot form (0: never)
+  size_t one_shot_bytes = 0;    // all-reduce buckets up to this many input bytes take the one-shot form (0 = never, the default:
+                                // measured slower than the two-shot form at W = 2, profiles/allreduce_r02.md)
   int k2_ag_mc = 0;             // sharded step publishes its shard with multimem.st (one store replicated by the switch)
   // device state
   std::vector<StepState> states;      // [0] is created with the context
