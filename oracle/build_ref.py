@@ -19,6 +19,13 @@ SRC = os.environ.get("STOKE_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 
 
+def _make_writable(root: str):
+    for d, _, files in os.walk(root):
+        os.chmod(d, 0o755)
+        for f in files:
+            os.chmod(os.path.join(d, f), 0o644)
+
+
 def build(verbose: bool = True) -> bool:
     src_pkg = os.path.join(SRC, "stoke")
     if not os.path.isdir(src_pkg):
@@ -27,9 +34,11 @@ def build(verbose: bool = True) -> bool:
         return os.path.isdir(os.path.join(DST, "stoke"))
     dst_pkg = os.path.join(DST, "stoke")
     if os.path.isdir(dst_pkg):
+        _make_writable(dst_pkg)
         shutil.rmtree(dst_pkg)
     os.makedirs(DST, exist_ok=True)
     shutil.copytree(src_pkg, dst_pkg, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    _make_writable(dst_pkg)   # the source tree is mounted read-only; the copy must stay removable
     with open(os.path.join(DST, "README"), "w") as f:
         f.write("Verbatim copy of /root/reference/stoke made by oracle/build_ref.py; git-ignored, test infrastructure only.\n")
     if verbose:
