@@ -32,6 +32,8 @@
  *   stk_grad_scale                   clip_grad_norm_'s scaling pass / clip_grad_value_ (stoke/fp16.py:184, 233) for the
  *                                    stock-optimizer route (any torch.optim class, stoke/extensions.py:53-78)
  *   stk_loss_sync_begin/_wait        detach_and_sync_loss without the per-micro-step host synchronisation
+ *   stk_optim_range_prologue         torch's per-parameter `state[p]["step"]` (torch/optim/adam.py: a parameter whose grad is None
+ *                                    is not stepped and keeps its own count) for models with sometimes-unused parameters
  */
 #ifndef STOKE_B200_H
 #define STOKE_B200_H
