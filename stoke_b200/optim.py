@@ -52,6 +52,13 @@ def _group_layout(module: torch.nn.Module, optim_kwargs: Dict):
     return params, group_of, extra, kw
 
 
+def state_dict_index(group_of: List[int], n_groups: int) -> Dict[int, int]:
+    """flat parameter position -> torch's ``state_dict()`` parameter id (torch numbers parameters group by group, in group
+    order: torch/optim/optimizer.py ``state_dict``)."""
+    order = [i for gi in range(n_groups) for i, g in enumerate(group_of) if g == gi]
+    return {flat_i: sd_i for sd_i, flat_i in enumerate(order)}
+
+
 def fused_supported(optim_cls, optim_kwargs: Dict, module: torch.nn.Module) -> bool:
     if optim_cls not in _KINDS:
         return False
@@ -98,8 +105,7 @@ class B200FusedOptimizer(torch.optim.Optimizer):
         super().__init__([dict(g, params=ps) for g, ps in zip(extra, by_group)], dict(probe.defaults))
         self._group_of = group_of
         # position of every parameter inside torch's state_dict numbering (group by group, in group order)
-        order = [i for gi in range(len(extra)) for i, g in enumerate(group_of) if g == gi]
-        self._sd_index = {flat_i: sd_i for sd_i, flat_i in enumerate(order)}
+        self._sd_index = state_dict_index(group_of, len(extra))
         engine.scaler_set(state=self.path.state_id, opt_steps=0, skipped_steps=0, found_inf=0, growth_tracker=0)
 
     # -- the step -------------------------------------------------------------------------------------------------------

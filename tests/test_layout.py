@@ -81,3 +81,31 @@ def test_resnet50_sized_plan():
     assert sum(b1 - b0 for b0, b1 in buckets) == n
     segs, n_local = layout.plan_segments(buckets, 8, True)
     assert sum(n_local) == n and max(n_local) - min(n_local) <= 16 * len(buckets) * 8
+
+
+def test_parameter_group_layout_matches_torch_numbering():
+    """``optim._group_layout`` + ``state_dict_index``: torch-style parameter groups given through ``optimizer_kwargs["params"]``
+    map every trainable parameter (registration order) to its group, and the fused optimizer's ``state_dict()`` numbers the
+    parameters exactly like the torch optimizer built from the same groups."""
+    import torch
+
+    from stoke_b200.optim import _group_layout, fused_supported, state_dict_index
+
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.LayerNorm(8), torch.nn.Linear(8, 2))
+    net[2].bias.requires_grad_(False)                       # frozen parameters are not part of the layout
+    decay = [p for n, p in net.named_parameters() if p.requires_grad and p.ndim > 1]
+    no_decay = [p for n, p in net.named_parameters() if p.requires_grad and p.ndim == 1]
+    kw = {"lr": 1e-3, "weight_decay": 0.1, "params": [{"params": no_decay, "weight_decay": 0.0}, {"params": decay}]}
+    params, group_of, extra, rest = _group_layout(net, kw)
+    assert [p.shape for p in params] == [p.shape for p in net.parameters() if p.requires_grad]
+    assert group_of == [1, 0, 0, 0, 1] and extra == [{"weight_decay": 0.0}, {}] and rest == {"lr": 1e-3, "weight_decay": 0.1}
+    # (torch writes the defaults INTO the group dicts it is given: hand it copies)
+    ref = torch.optim.AdamW([dict(g) for g in kw["params"]], lr=1e-3, weight_decay=0.1)
+    ids = {id(p): i for g in ref.param_groups for p, i in zip(g["params"], ref.state_dict()["param_groups"][ref.param_groups.index(g)]["params"])}
+    index = state_dict_index(group_of, len(extra))
+    assert [index[i] for i in range(len(params))] == [ids[id(p)] for p in params]
+    assert fused_supported(torch.optim.AdamW, kw, net)
+    assert not fused_supported(torch.optim.Adam, dict(kw, amsgrad=True), net)       # stock-optimizer route
+    assert not fused_supported(torch.optim.RMSprop, {"lr": 1e-3}, net)
+    with pytest.raises(ValueError):
+        _group_layout(net, {"params": [{"params": decay}]})                          # a trainable parameter left out
